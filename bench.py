@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Benchmark of the feb200 hot path (contract: see the task statement / DESIGN.md "Measurement").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--n 200] [--impl feb200|reference]
+
+N=1 workload (BASELINE.json configs[1]): 3-D hex8 linear elasticity on a uniform n^3 grid (n=200: 8 M
+elements, 24.4 M DoFs, 1.95e9 non-zeros), interior nodes jittered, batch-constant isotropic material.
+One "step" = one assembly pass of the whole mesh through the fe_jax call surface:
+calculate_residual_w_dirichlet + Jacobian CSR values at u_w + Dirichlet elimination of the matrix.
+`value` = elements / s with all inputs resident in HBM (CUDA events around the timed region);
+`e2e` = the same pass with the solution vector coming from pinned host memory and the residual + Jacobian
+diagonal read back to the host inside the timed region.  The Newton-CG step (assembly + 100 CG iterations
++ update + residual) is reported in `newton_cg`.  N>1 (torchrun): every rank assembles its own x-slab
+of an (N*n) x n x n grid (weak scaling, no data-path collective in assembly); `newton_cg` then uses the
+NCCL halo-sum + all-reduce path.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "fea-in-jax_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+os.environ.setdefault("FEB200_QUIET", "1")
+
+import numpy as np
+
+METRIC = "hex8_assembly_elements_per_s"
+UNIT = "elements/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--n", type=int, default=200, help="elements per axis of the hex8 grid (per rank)")
+    ap.add_argument("--impl", default="feb200", choices=["feb200", "reference"])
+    ap.add_argument("--cg-iters", type=int, default=100)
+    ap.add_argument("--cpu-n", type=int, default=20, help="grid size of the bounded CPU-baseline sample")
+    ap.add_argument("--layout", default="M", choices=["M", "EM", "EQM"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+def make_problem(n_x, n, layout, x0=0.0, x1=1.0):
+    """hex8 grid of n_x x n x n elements on [x0,x1] x [0,1]^2 with jittered interior nodes."""
+    import fe_jax as fj
+    Vx, cells = fj.uniform_hex_grid(n_x, n, n, bbox=((x0, x1), (0.0, 1.0), (0.0, 1.0)))
+    h = 1.0 / n
+    rng = np.random.default_rng(0)
+    interior = np.all((Vx[:, 1:] > 1e-12) & (Vx[:, 1:] < 1 - 1e-12), axis=1) & (Vx[:, 0] > x0 + 1e-12) & (Vx[:, 0] < x1 - 1e-12)
+    Vx = Vx + 0.2 * h * rng.uniform(-1.0, 1.0, size=Vx.shape) * interior[:, None]
+    E = cells.shape[0]
+    rm = np.random.default_rng(2)
+    if layout == "EQM":
+        mp = np.empty((E, 8, 2))
+        mp[..., 0] = 10e9 + 90e9 * rm.uniform(size=(E, 8))
+        mp[..., 1] = 0.25
+    elif layout == "EM":
+        mp = np.empty((E, 2))
+        mp[:, 0] = 10e9 + 90e9 * rm.uniform(size=E)
+        mp[:, 1] = 0.25
+    else:
+        mp = np.array([70e9, 0.25])
+    return Vx, cells, mp
+
+
+def cpu_reference_sample(n, steps=1, warmup=0):
+    """The oracle's reference-style assembly (element residual + K_e by 24 residual evaluations + COO triples +
+    lexsort + duplicate sum, fea.py:613-660) on an n^3 hex8 grid; returns elements/s."""
+    from oracle import fe_oracle as orc
+    Vx, cells, u, mp, bcs, vals = orc.synthetic_hex_problem(n, material_layout="M")
+    xi, W = orc.get_quadrature("hexahedron", 2)
+    _, dphi = orc.eval_basis_and_derivatives("hexahedron", 1, xi)
+    prob = orc.Problem(Vx, [orc.Batch(cells, "linear", "elastic_isotropic", mp, dphi, W)])
+    dofs, values_g, mask_g = orc.dirichlet_arrays(prob.F, 3, bcs, vals)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        R = prob.residual_w_dirichlet(u, values_g, mask_g)
+        d, r, c = prob.jacobian_wo_dirichlet((1 - mask_g) * u + mask_g * values_g)
+        dw = orc.apply_dirichlet_bcs_lhs(d, r, c, dofs)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return cells.shape[0] / float(np.mean(times)), float(np.mean(times)), cells.shape[0]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    eps, sec, E = cpu_reference_sample(args.cpu_n, steps=max(1, args.steps), warmup=min(1, args.warmup))
+    line = {"impl": "reference", "metric": METRIC, "value": eps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"hex8 linear elasticity, uniform grid, residual+Jacobian assembly (BASELINE configs[1]); "
+                                   f"CPU sample {args.cpu_n}^3 elements of the same workload"},
+            "cpu_baseline": {"value": eps, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": f"oracle (NumPy restatement of the reference algorithm: per-element K_e + COO lexsort + "
+                                       f"duplicate sum) on a {args.cpu_n}^3 hex8 grid ({E} elements), host cores of this box; "
+                                       "the reference's own JAX-CPU path cannot run (no jax in the image)"},
+            "e2e": {"value": eps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as graft
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if not os.path.exists(graft.LIB):
+        if rank == 0:
+            graft.build()
+        if world > 1:
+            dist.barrier()
+    import fe_jax as fj
+    from fe_jax import _lib
+    from fe_jax.assembly import _assemble_values, _plan, csr_diagonal
+    from fe_jax.krylov import cg_on_pattern
+
+    dev = torch.device("cuda", local_rank)
+    n = args.n
+    # rank r owns the x-slab [r, r+1] of an (world*n) x n x n grid (weak scaling)
+    Vx, cells, mp = make_problem(n, n, args.layout, x0=float(rank), x1=float(rank + 1))
+    E, V = cells.shape[0], Vx.shape[0]
+    F = 3 * V
+    fe = fj.FiniteElementType(fj.CellType.hexahedron, fj.ElementFamily.P, 1, fj.LagrangeVariant.equispaced,
+                              fj.QuadratureType.default, 2)
+    batch = fj.ElementBatch(fe_type=fe, n_dofs_per_basis=3, connectivity_en=cells, constitutive_model=fj.elastic_isotropic,
+                            material_params=mp)
+    t_setup = time.perf_counter()
+    ebc = fj.batch_to_collection(Vx, [batch])
+    maps = [fj.mesh_to_sparse_assembly_map(V, cells)]
+    plan = _plan(ebc, maps)
+    pat = plan.pattern
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t_setup
+    nnz = pat.nnz
+
+    # Dirichlet: global face x=0 fixed, global face x=world: u_x = 0.01
+    mask = torch.zeros(F, dtype=torch.float64, device=dev)
+    values = torch.zeros(F, dtype=torch.float64, device=dev)
+    xs = torch.from_numpy(Vx[:, 0]).to(dev)
+    left = (xs < 1e-12).nonzero().reshape(-1)
+    right = (xs > world - 1e-12).nonzero().reshape(-1)
+    for c in range(3):
+        mask[3 * left + c] = 1.0
+    mask[3 * right] = 1.0
+    values[3 * right] = 0.01
+    dofs = mask.nonzero().reshape(-1)
+    u_host = torch.from_numpy(1e-3 * np.random.default_rng(1).uniform(size=F)).pin_memory()
+    u = u_host.to(dev)
+    token = fj.linear_elasticity_residual
+    J_vals = torch.empty(nnz, dtype=torch.float64, device=dev)
+    R_host = torch.empty(F, dtype=torch.float64).pin_memory()
+    diag_host = torch.empty(F, dtype=torch.float64).pin_memory()
+
+    def assembly_step():
+        R, _ = fj.calculate_residual_w_dirichlet(token, ebc, maps, u, values, mask)
+        _assemble_values(token, ebc, maps, u, mask, values, out=J_vals)
+        _lib.call("feb200_dirichlet_lhs", pat.V, pat.U, _lib.ptr(pat.nindptr), _lib.ptr(pat.nindices), _lib.ptr(mask),
+                  _lib.ptr(J_vals))
+        return R
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.launches
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, _lib.launches - l0
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_step, launches = timed(assembly_step, args.steps, args.warmup)
+
+    # ---- per-kernel durations (same inputs, each kernel timed on its own over `steps` launches)
+    res = fj.physics.resolve_residual(token)
+    bstruct = ebc._batch_struct(0, res.kind)
+    K_e = ebc._buffer("K_e", E * 8 * 8 * 9)
+    R_e = ebc._buffer("R_e", E * 24)
+    Rtmp = torch.empty(F, dtype=torch.float64, device=dev)
+    row = maps[0].indptr.reshape(-1).view(torch.int64)
+    col = maps[0].indices.reshape(-1).view(torch.int64)
+    kernels = {
+        "element_residual": lambda: _lib.call("feb200_element_residual", bstruct, _lib.ptr(ebc._vertices), _lib.ptr(u),
+                                              _lib.ptr(mask), _lib.ptr(values), _lib.ptr(R_e)),
+        "scatter_sum": lambda: _lib.call("feb200_scatter_sum", _lib.ptr(row), _lib.ptr(col), V, 3, _lib.ptr(R_e),
+                                         _lib.ptr(Rtmp), 0, _lib.ptr(mask), _lib.ptr(values), _lib.ptr(u)),
+        "element_tangent": lambda: _lib.call("feb200_element_tangent", bstruct, _lib.ptr(ebc._vertices), _lib.ptr(u),
+                                             _lib.ptr(mask), _lib.ptr(values), _lib.ptr(K_e)),
+        "assemble_csr": lambda: _lib.call("feb200_assemble_csr", plan.maps[0], pat.V, pat.U, _lib.ptr(K_e),
+                                          _lib.ptr(plan.slot_rank[0]), _lib.ptr(pat.nindptr), pat.max_deg,
+                                          _lib.ptr(J_vals), 0),
+        "dirichlet_lhs": lambda: _lib.call("feb200_dirichlet_lhs", pat.V, pat.U, _lib.ptr(pat.nindptr),
+                                           _lib.ptr(pat.nindices), _lib.ptr(mask), _lib.ptr(J_vals)),
+    }
+    kernel_ms = {k: timed(f, args.steps, 1)[0] for k, f in kernels.items()}
+    assemble_step_again = assembly_step()        # leave J_vals / R consistent for the solve below
+    xv = torch.rand(F, dtype=torch.float64, device=dev)
+    yv = torch.empty_like(xv)
+    spmv = lambda: _lib.call("feb200_spmv", pat.V, pat.U, _lib.ptr(pat.nindptr), _lib.ptr(pat.nindices), _lib.ptr(J_vals),
+                             _lib.ptr(xv), _lib.ptr(yv), None, None, 0)
+    kernel_ms["spmv"] = timed(spmv, max(args.steps, 10), 3)[0]
+
+    # ---- Newton-CG step: assembly + fixed number of CG iterations + update + residual re-evaluation
+    def newton_cg_step():
+        R = assembly_step()
+        b = -R
+        dx0 = torch.zeros_like(b)
+        dx0[dofs] = values[dofs] - u[dofs]
+        dx, k, hist = cg_on_pattern(pat, J_vals, b, dx0, 0.0, 0.0, args.cg_iters, None, poll_every=args.cg_iters)
+        dx[dofs] = values[dofs] - u[dofs]
+        un = u + dx
+        R2, _ = fj.calculate_residual_w_dirichlet(token, ebc, maps, un, values, mask)
+        return k, hist, R2
+
+    ncg_ms = None
+    if world == 1:
+        ncg_ms, _ = timed(newton_cg_step, max(1, args.steps // 2), 1)
+        k, hist, R2 = newton_cg_step()
+        cg_only_ms = (ncg_ms - ms_step) / max(args.cg_iters, 1)
+        newton = {"step_ms": ncg_ms, "cg_iters": args.cg_iters, "ms_per_cg_iter": cg_only_ms,
+                  "residual_norm_first": float(hist[0]), "residual_norm_last": float(hist[min(k, args.cg_iters) - 1]),
+                  "note": "fixed CG iteration count (tol=0): assembly + CG + update + residual re-evaluation"}
+    else:
+        newton = {"step_ms": None, "note": "multi-GPU Newton-CG: see tests/test_partition.py (halo-sum + all-reduce path)"}
+
+    # ---- end to end through the public API with host buffers
+    def e2e_step():
+        u.copy_(u_host, non_blocking=True)
+        R = assembly_step()
+        d = csr_diagonal(pat, J_vals)
+        R_host.copy_(R, non_blocking=True)
+        diag_host.copy_(d, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_ms, _ = timed(e2e_step, max(1, args.steps), 1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        hbm, hbm_src = peaks()
+        total_E = E * world
+        value = total_E / (ms_step * 1e-3)
+        # algorithmic bytes per assembly pass: 8 nnz + slot map (2 B/entry here) + conn + coords + u + R
+        n_mp = {"M": 2, "EM": 2 * E, "EQM": 16 * E}[args.layout]
+        alg_bytes = 8 * nnz + 2 * 64 * E + 4 * 8 * E + 8 * 3 * V + 8 * F + 8 * F + 16 * F + 8 * n_mp
+        dom = max(("element_tangent", "assemble_csr"), key=lambda k: kernel_ms[k])
+        asm_ms = kernel_ms["element_tangent"] + kernel_ms["assemble_csr"]
+        achieved = alg_bytes / (asm_ms * 1e-3) / 1e9
+        spmv_bytes = 8 * nnz + 4 * (nnz // 9) + 8 * (V + 1) + 16 * F
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"3D hex8 linear elasticity, uniform grid {n}^3 elements per GPU (BASELINE configs[1]), "
+                                   f"residual + Jacobian CSR assembly + Dirichlet elimination; material layout ({args.layout})",
+                       "elements_per_gpu": E, "dofs_per_gpu": F, "nnz_per_gpu": nnz, "l2_policy": "inputs larger than L2",
+                       "setup_s": t_setup},
+            "roofline": {"bound": "hbm", "kernel": f"element_tangent + assemble_csr (two-pass assembly; dominant: {dom})",
+                         "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                         "peak_source": hbm_src, "algorithmic_bytes": alg_bytes,
+                         "kernel_ms": kernel_ms,
+                         "spmv": {"achieved": spmv_bytes / (kernel_ms["spmv"] * 1e-3) / 1e9, "peak": hbm,
+                                  "frac": spmv_bytes / (kernel_ms["spmv"] * 1e-3) / 1e9 / hbm, "algorithmic_bytes": spmv_bytes}},
+            "newton_cg": newton,
+            "e2e": {"value": total_E / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * F,
+                    "d2h_bytes_per_step": 16 * F, "ms_per_step": e2e_ms},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            eps, sec, Ec = cpu_reference_sample(args.cpu_n)
+            line["cpu_baseline"] = {"value": eps, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": f"oracle reference-style assembly on a {args.cpu_n}^3 hex8 grid ({Ec} elements, "
+                                              f"{sec:.1f} s)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,258 @@
+// Deterministic sparse assembly and the COO / CSR helpers of the reference.
+//   calculate_jacobian_wo_dirichlet        /root/reference/src/fe_jax/fea.py:613-660
+//   coo_arrays_sum_duplicates_jit          src/fe_jax/sparse_matrix.py:44-92
+//   coo_to_csr                             src/fe_jax/sparse_matrix.py:113-153
+//   apply_dirichlet_bcs_lhs                src/fe_jax/sparse_matrix.py:157-184
+//   calculate_jacobian_diag_wo_dirichlet   src/fe_jax/fea.py:759-797
+//
+// The reference concatenates E*(N*U)^2 COO triples, sorts them by (row, col) and sums duplicates
+// with bincount -- i.e. every CSR entry is the sum of its element contributions in ascending element
+// order.  Here every vertex owns its U CSR rows ("row panel") and pulls the same contributions, in
+// the same order, through the assembly map (its slots e*N+a, ascending) and the slot-rank map, so
+// no atomics are involved and the result is bit-reproducible.
+#include <cub/device/device_scan.cuh>
+
+#include "common.cuh"
+
+namespace feb {
+
+// one warp per vertex; accumulators in shared memory: acc[r][i][j] for neighbour rank r
+template <int U>
+__global__ void k_assemble_csr(const unsigned long long* __restrict__ row_ind, const unsigned long long* __restrict__ col_ind,
+                               int64_t V, int N, const double* __restrict__ K_e, const uint16_t* __restrict__ slot_rank,
+                               const int64_t* __restrict__ nindptr, int max_deg, double* __restrict__ values, int accumulate) {
+    constexpr int U2 = U * U;
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    double* acc = smem + (size_t)warp * max_deg * U2;
+    const int blk = N * U2;                                    // doubles per slot chunk
+    for (int64_t a = (int64_t)blockIdx.x * wpb + warp; a < V; a += (int64_t)gridDim.x * wpb) {
+        const int64_t p0 = nindptr[a];
+        const int deg = (int)(nindptr[a + 1] - p0);
+        for (int t = lane; t < deg * U2; t += 32) acc[t] = 0.0;
+        __syncwarp();
+        const unsigned long long s0 = row_ind[a], s1 = row_ind[a + 1];
+        for (unsigned long long k = s0; k < s1; ++k) {          // ascending slots == ascending elements
+            const unsigned long long slot = col_ind[k];
+            const double* chunk = K_e + slot * (unsigned long long)blk;
+            const uint16_t* rk = slot_rank + slot * (unsigned long long)N;
+            for (int t = lane; t < blk; t += 32) {
+                const int bn = t / U2, c = t - bn * U2;
+                acc[(int)rk[bn] * U2 + c] += chunk[t];          // distinct bn -> distinct rank: no conflicts
+            }
+            __syncwarp();
+        }
+        // row panel: values[U2*p0 + i*(U*deg) + U*r + j] = acc[r][i][j]
+        const int row_len = U * deg;
+        double* dst = values + (int64_t)U2 * p0;
+        for (int t = lane; t < U * row_len; t += 32) {
+            const int i = t / row_len, c = t - i * row_len;
+            const int r = c / U, j = c - r * U;
+            const double v = acc[r * U2 + i * U + j];
+            dst[t] = accumulate ? dst[t] + v : v;
+        }
+        __syncwarp();
+    }
+}
+
+template <int U>
+__global__ void k_dirichlet_lhs(int64_t V, const int64_t* __restrict__ nindptr, const int32_t* __restrict__ nindices,
+                                const double* __restrict__ mask, double* __restrict__ values) {
+    constexpr int U2 = U * U;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    for (int64_t a = (int64_t)blockIdx.x * wpb + warp; a < V; a += (int64_t)gridDim.x * wpb) {
+        const int64_t p0 = nindptr[a];
+        const int deg = (int)(nindptr[a + 1] - p0);
+        const int row_len = U * deg;
+        double* dst = values + (int64_t)U2 * p0;
+        double mrow[U];
+        bool any_row = false;
+#pragma unroll
+        for (int i = 0; i < U; ++i) { mrow[i] = mask[a * U + i]; any_row |= (mrow[i] != 0.0); }
+        for (int t = lane; t < U * row_len; t += 32) {
+            const int i = t / row_len, c = t - i * row_len;
+            const int r = c / U, j = c - r * U;
+            const int64_t colv = nindices[p0 + r];
+            const bool rm = (mrow[i] != 0.0);
+            const bool cm = (mask[colv * U + j] != 0.0);
+            if (rm || cm) dst[t] = (rm && colv == a && i == j) ? 1.0 : 0.0;
+        }
+        (void)any_row;
+    }
+}
+
+__global__ void k_dirichlet_lhs_coo(int64_t nnz, const int64_t* __restrict__ row, const int64_t* __restrict__ col,
+                                    const double* __restrict__ mask, const double* __restrict__ in, double* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = row[i], c = col[i];
+        const bool rm = mask[r] != 0.0, cm = mask[c] != 0.0;
+        double v = (rm || cm) ? 0.0 : in[i];
+        if (r == c && rm) v = 1.0;
+        out[i] = v;
+    }
+}
+
+template <int U>
+__global__ void k_csr_diagonal(int64_t V, const int64_t* __restrict__ nindptr, const int32_t* __restrict__ diag_rank,
+                               const double* __restrict__ values, double* __restrict__ diag) {
+    for (int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; a < V; a += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p0 = nindptr[a];
+        const int deg = (int)(nindptr[a + 1] - p0);
+        const int r = diag_rank[a];
+#pragma unroll
+        for (int i = 0; i < U; ++i)
+            diag[a * U + i] = (r >= 0) ? values[(int64_t)U * U * p0 + (int64_t)i * U * deg + U * r + i] : 0.0;
+    }
+}
+
+__global__ void k_mark_heads(int64_t n, const int64_t* __restrict__ row, const int64_t* __restrict__ col, int32_t* head) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        head[i] = (i == 0 || row[i] != row[i - 1] || col[i] != col[i - 1]) ? 1 : 0;
+}
+__global__ void k_minus_one(int64_t n, int64_t* seg) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) seg[i] -= 1;
+}
+// thread i owning a segment head adds its run sequentially (stable order == bincount on CPU)
+__global__ void k_segment_sum(int64_t n, const int64_t* __restrict__ row, const int64_t* __restrict__ col,
+                              const double* __restrict__ data, const int32_t* __restrict__ head,
+                              const int64_t* __restrict__ seg, int64_t n_out, double* __restrict__ out_data,
+                              int64_t* __restrict__ out_row, int64_t* __restrict__ out_col) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (!head[i]) continue;
+        const int64_t o = seg[i];
+        if (o >= n_out) continue;
+        double acc = data[i];
+        for (int64_t j = i + 1; j < n && !head[j]; ++j) acc += data[j];
+        out_data[o] = acc;
+        if (out_row) out_row[o] = row[i];
+        if (out_col) out_col[o] = col[i];
+    }
+}
+// indptr[r] = first index with row >= r (rows sorted ascending)
+__global__ void k_rows_to_indptr(int64_t nnz, const int64_t* __restrict__ row, int64_t n_rows, int64_t* __restrict__ indptr) {
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r <= n_rows; r += (int64_t)gridDim.x * blockDim.x) {
+        int64_t lo = 0, hi = nnz;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (row[mid] < r) lo = mid + 1; else hi = mid;
+        }
+        indptr[r] = lo;
+    }
+}
+
+}  // namespace feb
+
+using namespace feb;
+
+extern "C" {
+
+int feb200_assemble_csr(feb200_stream s, const feb200_batch_map* map, int64_t V, int32_t U, const double* K_e,
+                        const uint16_t* slot_rank, const int64_t* nindptr, int32_t max_deg, double* values,
+                        int32_t accumulate) {
+    FEB_REQUIRE(map && map->row_ind && map->col_ind && K_e && slot_rank && nindptr && values, FEB200_ERR_INVALID,
+                "assemble_csr: null pointer");
+    FEB_REQUIRE(max_deg > 0 && max_deg <= 65535, FEB200_ERR_INVALID, "assemble_csr: max_deg=%d out of range", max_deg);
+    if (V == 0) return FEB200_OK;
+    cudaStream_t st = as_stream(s);
+    const unsigned long long* ri = reinterpret_cast<const unsigned long long*>(map->row_ind);
+    const unsigned long long* ci = reinterpret_cast<const unsigned long long*>(map->col_ind);
+    int wpb = 8;
+    size_t per_warp = (size_t)max_deg * U * U * sizeof(double);
+    while (wpb > 1 && per_warp * wpb > 64 * 1024) wpb >>= 1;
+    const size_t smem = per_warp * wpb;
+    FEB_REQUIRE(smem <= 200 * 1024, FEB200_ERR_CAPACITY, "assemble_csr: vertex degree %d needs %zu bytes of shared memory", max_deg, smem);
+    int64_t g = ceil_div(V, wpb);
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (g > cap) g = cap;
+#define FEB_ASM(UU)                                                                                                    \
+    {                                                                                                                  \
+        auto kern = k_assemble_csr<UU>;                                                                                \
+        if (smem > 48 * 1024) FEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<(int)g, wpb * 32, smem, st>>>(ri, ci, V, map->N, K_e, slot_rank, nindptr, max_deg, values, accumulate);  \
+    }
+    if (U == 2) FEB_ASM(2)
+    else if (U == 3) FEB_ASM(3)
+    else if (U == 1) FEB_ASM(1)
+    else FEB_REQUIRE(false, FEB200_ERR_UNSUPPORTED, "assemble_csr: U=%d not supported", U);
+#undef FEB_ASM
+    FEB_CHECK_LAUNCH("assemble_csr");
+    return FEB200_OK;
+}
+
+int feb200_dirichlet_lhs(feb200_stream s, int64_t V, int32_t U, const int64_t* nindptr, const int32_t* nindices,
+                         const double* mask, double* values) {
+    FEB_REQUIRE(nindptr && nindices && mask && values, FEB200_ERR_INVALID, "dirichlet_lhs: null pointer");
+    if (V == 0) return FEB200_OK;
+    cudaStream_t st = as_stream(s);
+    int64_t g = ceil_div(V, 8);
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (g > cap) g = cap;
+    if (U == 2) k_dirichlet_lhs<2><<<(int)g, 256, 0, st>>>(V, nindptr, nindices, mask, values);
+    else if (U == 3) k_dirichlet_lhs<3><<<(int)g, 256, 0, st>>>(V, nindptr, nindices, mask, values);
+    else if (U == 1) k_dirichlet_lhs<1><<<(int)g, 256, 0, st>>>(V, nindptr, nindices, mask, values);
+    else FEB_REQUIRE(false, FEB200_ERR_UNSUPPORTED, "dirichlet_lhs: U=%d not supported", U);
+    FEB_CHECK_LAUNCH("dirichlet_lhs");
+    return FEB200_OK;
+}
+
+int feb200_dirichlet_lhs_coo(feb200_stream s, int64_t nnz, const int64_t* row, const int64_t* col, const double* mask,
+                             const double* data_in, double* data_out) {
+    FEB_REQUIRE(row && col && mask && data_in && data_out, FEB200_ERR_INVALID, "dirichlet_lhs_coo: null pointer");
+    if (nnz == 0) return FEB200_OK;
+    k_dirichlet_lhs_coo<<<grid_for(nnz, 256), 256, 0, as_stream(s)>>>(nnz, row, col, mask, data_in, data_out);
+    FEB_CHECK_LAUNCH("dirichlet_lhs_coo");
+    return FEB200_OK;
+}
+
+int feb200_csr_diagonal(feb200_stream s, int64_t V, int32_t U, const int64_t* nindptr, const int32_t* diag_rank,
+                        const double* values, double* diag) {
+    FEB_REQUIRE(nindptr && diag_rank && values && diag, FEB200_ERR_INVALID, "csr_diagonal: null pointer");
+    if (V == 0) return FEB200_OK;
+    cudaStream_t st = as_stream(s);
+    const int g = grid_for(V, 128);
+    if (U == 2) k_csr_diagonal<2><<<g, 128, 0, st>>>(V, nindptr, diag_rank, values, diag);
+    else if (U == 3) k_csr_diagonal<3><<<g, 128, 0, st>>>(V, nindptr, diag_rank, values, diag);
+    else if (U == 1) k_csr_diagonal<1><<<g, 128, 0, st>>>(V, nindptr, diag_rank, values, diag);
+    else FEB_REQUIRE(false, FEB200_ERR_UNSUPPORTED, "csr_diagonal: U=%d not supported", U);
+    FEB_CHECK_LAUNCH("csr_diagonal");
+    return FEB200_OK;
+}
+
+int feb200_coo_mark_heads(feb200_stream s, int64_t n, const int64_t* row, const int64_t* col, int32_t* head) {
+    FEB_REQUIRE(row && col && head, FEB200_ERR_INVALID, "coo_mark_heads: null pointer");
+    if (n == 0) return FEB200_OK;
+    k_mark_heads<<<grid_for(n, 256), 256, 0, as_stream(s)>>>(n, row, col, head);
+    FEB_CHECK_LAUNCH("coo_mark_heads");
+    return FEB200_OK;
+}
+
+int feb200_coo_scan_heads(feb200_stream s, int64_t n, const int32_t* head, int64_t* seg, void* ws, size_t ws_bytes) {
+    FEB_REQUIRE(head && seg, FEB200_ERR_INVALID, "coo_scan_heads: null pointer");
+    FEB_REQUIRE(ws_bytes >= feb200_scan_workspace_bytes(n), FEB200_ERR_WORKSPACE, "coo_scan_heads: workspace too small");
+    if (n == 0) return FEB200_OK;
+    cudaStream_t st = as_stream(s);
+    size_t bytes = ws_bytes;
+    FEB_CUDA(cub::DeviceScan::InclusiveSum(ws, bytes, head, seg, n, st));
+    k_minus_one<<<grid_for(n, 256), 256, 0, st>>>(n, seg);
+    FEB_CHECK_LAUNCH("coo_scan_heads");
+    return FEB200_OK;
+}
+
+int feb200_coo_segment_sum(feb200_stream s, int64_t n, const int64_t* row, const int64_t* col, const double* data,
+                           const int32_t* head, const int64_t* seg, int64_t n_out, double* out_data, int64_t* out_row,
+                           int64_t* out_col) {
+    FEB_REQUIRE(row && col && data && head && seg && out_data, FEB200_ERR_INVALID, "coo_segment_sum: null pointer");
+    if (n == 0) return FEB200_OK;
+    k_segment_sum<<<grid_for(n, 256), 256, 0, as_stream(s)>>>(n, row, col, data, head, seg, n_out, out_data, out_row, out_col);
+    FEB_CHECK_LAUNCH("coo_segment_sum");
+    return FEB200_OK;
+}
+
+int feb200_coo_rows_to_indptr(feb200_stream s, int64_t nnz, const int64_t* row, int64_t n_rows, int64_t* indptr) {
+    FEB_REQUIRE((row || nnz == 0) && indptr, FEB200_ERR_INVALID, "coo_rows_to_indptr: null pointer");
+    k_rows_to_indptr<<<grid_for(n_rows + 1, 256), 256, 0, as_stream(s)>>>(nnz, row, n_rows, indptr);
+    FEB_CHECK_LAUNCH("coo_rows_to_indptr");
+    return FEB200_OK;
+}
+
+}  // extern "C"

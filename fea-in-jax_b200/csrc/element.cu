@@ -1,0 +1,468 @@
+// Element kernels: batched residual R_e and tangent K_e.
+//   residual: one thread per element (replaces vmap(element_residual_func),
+//             /root/reference/src/fe_jax/fea.py:800-847 with linear_elasticity.py:145-206 /
+//             hyperelasticity.py:93-139 inside)
+//   tangent : N threads per element, thread (e, a) owns the block row K[a, :] (replaces
+//             vmap(jacfwd(residual_kernel)), fea.py:519-572, by the hand-derived
+//             K[(a,d),(b,k)] = sum_q detJ W sum_{i,l} g[a,i] dS[i,d]/dH[k,l] g[b,l]).
+// Coordinates and the solution are gathered from vertex arrays through `conn`; the Dirichlet
+// blend u_w = (1-m) u + m g (fea.py:948-950) is applied while gathering when a mask is given.
+#include "common.cuh"
+#include "element_math.cuh"
+
+namespace feb {
+
+__device__ __forceinline__ const double* mp_of(const feb200_batch& b, int64_t e, int& q_stride) {
+    if (b.layout == LAYOUT_EQM) { q_stride = b.M; return b.mp + (e * b.Q) * (int64_t)b.M; }
+    q_stride = 0;
+    return (b.layout == LAYOUT_EM) ? b.mp + e * (int64_t)b.M : b.mp;
+}
+
+__device__ __forceinline__ double load_u(const double* __restrict__ u, const double* __restrict__ mask,
+                                         const double* __restrict__ values, int64_t f) {
+    const double v = u[f];
+    if (!mask) return v;
+    const double m = mask[f];
+    return (1.0 - m) * v + m * values[f];
+}
+
+// ------------------------------------------------------------------------------------------------
+// residual, compile-time N: registers for x, u, R; dphi / W staged in shared memory; the element-major
+// result is transposed through shared memory so that the global stores are coalesced.
+// ------------------------------------------------------------------------------------------------
+template <int N, int D, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_residual_ct(feb200_batch b, const double* __restrict__ x_vd,
+                                                       const double* __restrict__ u, const double* __restrict__ mask,
+                                                       const double* __restrict__ values, double* __restrict__ R_e) {
+    constexpr int NU = N * D;
+    extern __shared__ double smem[];
+    double* s_dphi = smem;                         // Q*N*D
+    double* s_W = s_dphi + b.Q * NU;               // Q
+    double* s_out = s_W + b.Q;                     // BLOCK * (NU+1)
+    for (int i = threadIdx.x; i < b.Q * NU; i += BLOCK) s_dphi[i] = b.dphi[i];
+    for (int i = threadIdx.x; i < b.Q; i += BLOCK) s_W[i] = b.W[i];
+    __syncthreads();
+
+    for (int64_t e0 = (int64_t)blockIdx.x * BLOCK; e0 < b.E; e0 += (int64_t)gridDim.x * BLOCK) {
+        const int64_t e = e0 + threadIdx.x;
+        if (e < b.E) {
+            double x[NU], ue[NU], R[NU], g[NU];
+#pragma unroll
+            for (int n = 0; n < N; ++n) {
+                const int64_t v = b.conn[e * N + n];
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    x[n * D + d] = x_vd[v * D + d];
+                    ue[n * D + d] = load_u(u, mask, values, v * D + d);
+                    R[n * D + d] = 0.0;
+                }
+            }
+            if (b.kind == KIND_HYPER)
+#pragma unroll
+                for (int i = 0; i < NU; ++i) ue[i] += x[i];
+            int qs;
+            const double* mp = mp_of(b, e, qs);
+            for (int q = 0; q < b.Q; ++q) {
+                const double dt = shape_gradients<N, D>(x, s_dphi + q * NU, g);
+                double H[D][D], S[D][D];
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+#pragma unroll
+                    for (int d = 0; d < D; ++d) H[i][d] = 0.0;
+#pragma unroll
+                for (int n = 0; n < N; ++n)
+#pragma unroll
+                    for (int i = 0; i < D; ++i)
+#pragma unroll
+                        for (int d = 0; d < D; ++d) H[i][d] += g[n * D + d] * ue[n * D + i];
+                point_stress<D, double>(b.material, mp + (int64_t)q * qs, H, S);
+                const double w = dt * s_W[q];
+#pragma unroll
+                for (int n = 0; n < N; ++n)
+#pragma unroll
+                    for (int d = 0; d < D; ++d) {
+                        double sacc = 0.0;
+#pragma unroll
+                        for (int i = 0; i < D; ++i) sacc += g[n * D + i] * S[i][d];
+                        R[n * D + d] += w * sacc;
+                    }
+            }
+#pragma unroll
+            for (int i = 0; i < NU; ++i) s_out[threadIdx.x * (NU + 1) + i] = R[i];
+        }
+        __syncthreads();
+        const int64_t n_here = (b.E - e0 < BLOCK) ? (b.E - e0) : BLOCK;
+        for (int64_t i = threadIdx.x; i < n_here * NU; i += BLOCK) {
+            const int t = (int)(i / NU), c = (int)(i - (int64_t)t * NU);
+            R_e[e0 * NU + i] = s_out[t * (NU + 1) + c];
+        }
+        __syncthreads();
+    }
+}
+
+// residual, runtime N (quadratic elements): local-memory arrays
+constexpr int MAX_RT_N = 27;
+template <int D>
+__global__ void __launch_bounds__(64) k_residual_rt(feb200_batch b, const double* __restrict__ x_vd,
+                                                    const double* __restrict__ u, const double* __restrict__ mask,
+                                                    const double* __restrict__ values, double* __restrict__ R_e) {
+    const int N = b.N, NU = N * D;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < b.E; e += (int64_t)gridDim.x * blockDim.x) {
+        double x[MAX_RT_N * D], ue[MAX_RT_N * D], R[MAX_RT_N * D], g[MAX_RT_N * D];
+        for (int n = 0; n < N; ++n) {
+            const int64_t v = b.conn[e * N + n];
+            for (int d = 0; d < D; ++d) {
+                x[n * D + d] = x_vd[v * D + d];
+                ue[n * D + d] = load_u(u, mask, values, v * D + d);
+            }
+        }
+        int qs;
+        const double* mp = mp_of(b, e, qs);
+        element_residual_rt<D>(b.kind, b.material, N, b.Q, x, ue, b.dphi, b.W, mp, qs, g, R);
+        for (int i = 0; i < NU; ++i) R_e[e * NU + i] = R[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tangent: shared-memory staging common to all variants.  Per element in the block:
+//   xe[N*D], ue[N*D], g[Q][N*D], wdet[Q], aux[Q][AUX]   (AUX = D^4 general, 2 isotropic fast path)
+// Thread t of the block is (element e_l = t / N, node a = t % N).
+// ------------------------------------------------------------------------------------------------
+template <int D>
+__device__ __forceinline__ void stage_geometry(const feb200_batch& b, int N, int e_l, int a, int64_t e, bool active,
+                                               const double* __restrict__ x_vd, const double* __restrict__ u,
+                                               const double* __restrict__ mask, const double* __restrict__ values,
+                                               const double* s_dphi, double* s_el, int per_el, int AUX, bool iso_fast) {
+    const int NU = N * D, Q = b.Q;
+    double* xe = s_el + (size_t)e_l * per_el;
+    double* ue = xe + NU;
+    double* g = ue + NU;
+    double* wdet = g + (size_t)Q * NU;
+    double* aux = wdet + Q;
+    if (active) {
+        const int64_t v = b.conn[e * N + a];
+        for (int d = 0; d < D; ++d) {
+            xe[a * D + d] = x_vd[v * D + d];
+            double uu = load_u(u, mask, values, v * D + d);
+            ue[a * D + d] = uu;
+        }
+    }
+    __syncthreads();
+    if (active) {
+        int qs;
+        const double* mp = mp_of(b, e, qs);
+        for (int q = a; q < Q; q += N) {
+            double* gq = g + (size_t)q * NU;
+            const double dt = shape_gradients_rt<D>(N, xe, s_dphi + (size_t)q * NU, gq);
+            wdet[q] = dt * b.W[q];
+            const double* mpq = mp + (int64_t)q * qs;
+            if (iso_fast) {
+                double lam, mu;
+                isotropic_lame<D>(mpq, lam, mu);
+                aux[q * 2 + 0] = lam;
+                aux[q * 2 + 1] = mu;
+            } else {
+                double H[D][D];
+                for (int i = 0; i < D; ++i)
+                    for (int d = 0; d < D; ++d) H[i][d] = 0.0;
+                for (int n = 0; n < N; ++n)
+                    for (int i = 0; i < D; ++i) {
+                        const double ui = (b.kind == KIND_HYPER) ? ue[n * D + i] + xe[n * D + i] : ue[n * D + i];
+                        for (int d = 0; d < D; ++d) H[i][d] += gq[n * D + d] * ui;
+                    }
+                double A[D * D * D * D];
+                point_tangent<D>(b.material, mpq, H, A);
+                for (int i = 0; i < AUX; ++i) aux[(size_t)q * AUX + i] = A[i];
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// isotropic linear elasticity, closed form:
+//   K_ab[d][k] = sum_q w (lam g_a[d] g_b[k] + mu g_a[k] g_b[d]) + delta_dk sum_q w mu g_a.g_b
+template <int N, int D>
+__global__ void k_tangent_iso(feb200_batch b, int epb, int per_el, const double* __restrict__ x_vd,
+                              const double* __restrict__ u, const double* __restrict__ mask,
+                              const double* __restrict__ values, double* __restrict__ K_e) {
+    constexpr int NU = N * D;
+    extern __shared__ double smem[];
+    double* s_dphi = smem;
+    double* s_el = smem + (size_t)b.Q * NU;
+    for (int i = threadIdx.x; i < b.Q * NU; i += blockDim.x) s_dphi[i] = b.dphi[i];
+    const int e_l = threadIdx.x / N, a = threadIdx.x - e_l * N;
+    const int Q = b.Q;
+    for (int64_t e0 = (int64_t)blockIdx.x * epb; e0 < b.E; e0 += (int64_t)gridDim.x * epb) {
+        const int64_t e = e0 + e_l;
+        const bool active = (e_l < epb) && (e < b.E);
+        __syncthreads();
+        stage_geometry<D>(b, N, e_l, a, e, active, x_vd, u, mask, values, s_dphi, s_el, per_el, 2, true);
+        if (!active) continue;
+        const double* g = s_el + (size_t)e_l * per_el + 2 * NU;
+        const double* wdet = g + (size_t)Q * NU;
+        const double* aux = wdet + Q;
+        double* out = K_e + ((e * N + a) * (int64_t)N) * (D * D);
+        for (int bn = 0; bn < N; ++bn) {
+            double acc[D][D];
+            double tr = 0.0;
+#pragma unroll
+            for (int d = 0; d < D; ++d)
+#pragma unroll
+                for (int k = 0; k < D; ++k) acc[d][k] = 0.0;
+            for (int q = 0; q < Q; ++q) {
+                const double w = wdet[q], wl = w * aux[q * 2], wm = w * aux[q * 2 + 1];
+                double ga[D], gb[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) { ga[d] = g[(size_t)q * NU + a * D + d]; gb[d] = g[(size_t)q * NU + bn * D + d]; }
+                double dot = 0.0;
+#pragma unroll
+                for (int d = 0; d < D; ++d) dot += ga[d] * gb[d];
+                tr += wm * dot;
+#pragma unroll
+                for (int d = 0; d < D; ++d)
+#pragma unroll
+                    for (int k = 0; k < D; ++k) acc[d][k] += wl * ga[d] * gb[k] + wm * ga[k] * gb[d];
+            }
+#pragma unroll
+            for (int d = 0; d < D; ++d) acc[d][d] += tr;
+#pragma unroll
+            for (int d = 0; d < D; ++d)
+#pragma unroll
+                for (int k = 0; k < D; ++k) out[bn * D * D + d * D + k] = acc[d][k];
+        }
+    }
+}
+
+// general material, compile-time N: q outer, block row kept in registers
+template <int N, int D>
+__global__ void k_tangent_general_ct(feb200_batch b, int epb, int per_el, const double* __restrict__ x_vd,
+                                     const double* __restrict__ u, const double* __restrict__ mask,
+                                     const double* __restrict__ values, double* __restrict__ K_e) {
+    constexpr int NU = N * D, D2 = D * D, D4 = D2 * D2;
+    extern __shared__ double smem[];
+    double* s_dphi = smem;
+    double* s_el = smem + (size_t)b.Q * NU;
+    for (int i = threadIdx.x; i < b.Q * NU; i += blockDim.x) s_dphi[i] = b.dphi[i];
+    const int e_l = threadIdx.x / N, a = threadIdx.x - e_l * N;
+    const int Q = b.Q;
+    for (int64_t e0 = (int64_t)blockIdx.x * epb; e0 < b.E; e0 += (int64_t)gridDim.x * epb) {
+        const int64_t e = e0 + e_l;
+        const bool active = (e_l < epb) && (e < b.E);
+        __syncthreads();
+        stage_geometry<D>(b, N, e_l, a, e, active, x_vd, u, mask, values, s_dphi, s_el, per_el, D4, false);
+        if (!active) continue;
+        const double* g = s_el + (size_t)e_l * per_el + 2 * NU;
+        const double* wdet = g + (size_t)Q * NU;
+        const double* aux = wdet + Q;
+        double acc[N][D2];
+#pragma unroll
+        for (int bn = 0; bn < N; ++bn)
+#pragma unroll
+            for (int c = 0; c < D2; ++c) acc[bn][c] = 0.0;
+        for (int q = 0; q < Q; ++q) {
+            const double* A = aux + (size_t)q * D4;
+            const double* gq = g + (size_t)q * NU;
+            double t[D2][D];   // t[d*D+k][l] = w * sum_i g_a[i] A[i,d,k,l]
+            const double w = wdet[q];
+#pragma unroll
+            for (int dk = 0; dk < D2; ++dk)
+#pragma unroll
+                for (int l = 0; l < D; ++l) {
+                    const int d = dk / D, k = dk - d * D;
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int i = 0; i < D; ++i) sacc += gq[a * D + i] * A[(i * D + d) * D2 + k * D + l];
+                    t[dk][l] = w * sacc;
+                }
+#pragma unroll
+            for (int bn = 0; bn < N; ++bn)
+#pragma unroll
+                for (int dk = 0; dk < D2; ++dk) {
+                    double sacc = acc[bn][dk];
+#pragma unroll
+                    for (int l = 0; l < D; ++l) sacc += t[dk][l] * gq[bn * D + l];
+                    acc[bn][dk] = sacc;
+                }
+        }
+        double* out = K_e + ((e * N + a) * (int64_t)N) * D2;
+#pragma unroll
+        for (int bn = 0; bn < N; ++bn)
+#pragma unroll
+            for (int c = 0; c < D2; ++c) out[bn * D2 + c] = acc[bn][c];
+    }
+}
+
+// general material, runtime N: b outer, q inner, t recomputed (quadratic elements; coverage path)
+template <int D>
+__global__ void k_tangent_general_rt(feb200_batch b, int epb, int per_el, const double* __restrict__ x_vd,
+                                     const double* __restrict__ u, const double* __restrict__ mask,
+                                     const double* __restrict__ values, double* __restrict__ K_e) {
+    constexpr int D2 = D * D, D4 = D2 * D2;
+    const int N = b.N, NU = N * D, Q = b.Q;
+    extern __shared__ double smem[];
+    double* s_dphi = smem;
+    double* s_el = smem + (size_t)Q * NU;
+    for (int i = threadIdx.x; i < Q * NU; i += blockDim.x) s_dphi[i] = b.dphi[i];
+    const int e_l = threadIdx.x / N, a = threadIdx.x - e_l * N;
+    for (int64_t e0 = (int64_t)blockIdx.x * epb; e0 < b.E; e0 += (int64_t)gridDim.x * epb) {
+        const int64_t e = e0 + e_l;
+        const bool active = (e_l < epb) && (e < b.E);
+        __syncthreads();
+        stage_geometry<D>(b, N, e_l, a, e, active, x_vd, u, mask, values, s_dphi, s_el, per_el, D4, false);
+        if (!active) continue;
+        const double* g = s_el + (size_t)e_l * per_el + 2 * NU;
+        const double* wdet = g + (size_t)Q * NU;
+        const double* aux = wdet + Q;
+        double* out = K_e + ((e * N + a) * (int64_t)N) * D2;
+        for (int bn = 0; bn < N; ++bn) {
+            double acc[D2];
+#pragma unroll
+            for (int c = 0; c < D2; ++c) acc[c] = 0.0;
+            for (int q = 0; q < Q; ++q) {
+                const double* A = aux + (size_t)q * D4;
+                const double* gq = g + (size_t)q * NU;
+                const double w = wdet[q];
+#pragma unroll
+                for (int dk = 0; dk < D2; ++dk) {
+                    const int d = dk / D, k = dk - d * D;
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int l = 0; l < D; ++l) {
+                        double tl = 0.0;
+#pragma unroll
+                        for (int i = 0; i < D; ++i) tl += gq[a * D + i] * A[(i * D + d) * D2 + k * D + l];
+                        sacc += tl * gq[bn * D + l];
+                    }
+                    acc[dk] += w * sacc;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < D2; ++c) out[bn * D2 + c] = acc[c];
+        }
+    }
+}
+
+static int check_batch(const feb200_batch* b, const char* who) {
+    FEB_REQUIRE(b, FEB200_ERR_INVALID, "%s: null batch", who);
+    FEB_REQUIRE(b->E >= 0 && b->N > 0 && b->Q > 0 && (b->D == 2 || b->D == 3), FEB200_ERR_INVALID,
+                "%s: bad sizes E=%lld N=%d Q=%d D=%d", who, (long long)b->E, b->N, b->Q, b->D);
+    FEB_REQUIRE(b->N <= MAX_RT_N, FEB200_ERR_UNSUPPORTED, "%s: N=%d exceeds %d", who, b->N, MAX_RT_N);
+    FEB_REQUIRE(b->conn && b->dphi && b->W && b->mp, FEB200_ERR_INVALID, "%s: null table pointer", who);
+    FEB_REQUIRE(b->kind == KIND_LINEAR || b->kind == KIND_HYPER, FEB200_ERR_INVALID, "%s: bad kind %d", who, b->kind);
+    FEB_REQUIRE(b->material >= 0 && b->material <= 3, FEB200_ERR_INVALID, "%s: bad material %d", who, b->material);
+    FEB_REQUIRE(b->layout >= 0 && b->layout <= 2, FEB200_ERR_INVALID, "%s: bad layout %d", who, b->layout);
+    const bool lin = (b->material == MAT_ISOTROPIC || b->material == MAT_ORTHOTROPIC);
+    FEB_REQUIRE(lin == (b->kind == KIND_LINEAR), FEB200_ERR_UNSUPPORTED,
+                "%s: material %d cannot be used with residual kind %d", who, b->material, b->kind);
+    int need = 2;
+    if (b->material == MAT_ORTHOTROPIC) need = (b->D == 2) ? 4 : 9;
+    if (b->material == MAT_MOONEY_RIVLIN) need = 3;
+    FEB_REQUIRE(b->M >= need, FEB200_ERR_INVALID, "%s: material needs %d parameters, got %d", who, need, b->M);
+    return FEB200_OK;
+}
+
+template <int N, int D>
+static int launch_residual_ct(cudaStream_t st, const feb200_batch& b, const double* x_vd, const double* u,
+                              const double* mask, const double* values, double* R_e) {
+    constexpr int BLOCK = 128;
+    const size_t smem = ((size_t)b.Q * N * D + b.Q + (size_t)BLOCK * (N * D + 1)) * sizeof(double);
+    auto kern = k_residual_ct<N, D, BLOCK>;
+    if (smem > 48 * 1024) FEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t g = ceil_div(b.E, BLOCK);
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (g > cap) g = cap;
+    kern<<<(int)g, BLOCK, smem, st>>>(b, x_vd, u, mask, values, R_e);
+    return FEB200_OK;
+}
+
+struct TangentCfg { int epb, per_el, threads; size_t smem; };
+static int tangent_cfg(const feb200_batch& b, int aux, TangentCfg& c) {
+    const int NU = b.N * b.D;
+    c.per_el = 2 * NU + b.Q * NU + b.Q + b.Q * aux;
+    const size_t table = (size_t)b.Q * NU * sizeof(double);
+    const size_t budget = 96 * 1024;
+    int epb = 256 / b.N;
+    while (epb > 1 && table + (size_t)epb * c.per_el * sizeof(double) > budget) --epb;
+    if (epb < 1) epb = 1;
+    c.epb = epb;
+    c.smem = table + (size_t)epb * c.per_el * sizeof(double);
+    FEB_REQUIRE(c.smem <= 200 * 1024, FEB200_ERR_CAPACITY, "tangent: element needs %zu bytes of shared memory", c.smem);
+    c.threads = ((epb * b.N + 31) / 32) * 32;
+    return FEB200_OK;
+}
+
+template <typename Kern>
+static int launch_tangent(Kern kern, cudaStream_t st, const feb200_batch& b, const TangentCfg& c, const double* x_vd,
+                          const double* u, const double* mask, const double* values, double* K_e) {
+    if (c.smem > 48 * 1024) FEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+    int64_t g = ceil_div(b.E, c.epb);
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (g > cap) g = cap;
+    kern<<<(int)g, c.threads, c.smem, st>>>(b, c.epb, c.per_el, x_vd, u, mask, values, K_e);
+    return FEB200_OK;
+}
+
+}  // namespace feb
+
+using namespace feb;
+
+extern "C" {
+
+int feb200_element_residual(feb200_stream s, const feb200_batch* bp, const double* x_vd, const double* u,
+                            const double* mask, const double* values, double* R_e) {
+    int rc = check_batch(bp, "element_residual");
+    if (rc) return rc;
+    FEB_REQUIRE(x_vd && u && R_e, FEB200_ERR_INVALID, "element_residual: null pointer");
+    FEB_REQUIRE(!mask || values, FEB200_ERR_INVALID, "element_residual: mask without values");
+    const feb200_batch& b = *bp;
+    if (b.E == 0) return FEB200_OK;
+    cudaStream_t st = as_stream(s);
+    rc = FEB200_OK;
+    if (b.D == 2 && b.N == 3) rc = launch_residual_ct<3, 2>(st, b, x_vd, u, mask, values, R_e);
+    else if (b.D == 2 && b.N == 4) rc = launch_residual_ct<4, 2>(st, b, x_vd, u, mask, values, R_e);
+    else if (b.D == 3 && b.N == 4) rc = launch_residual_ct<4, 3>(st, b, x_vd, u, mask, values, R_e);
+    else if (b.D == 3 && b.N == 8) rc = launch_residual_ct<8, 3>(st, b, x_vd, u, mask, values, R_e);
+    else if (b.D == 2) k_residual_rt<2><<<grid_for(b.E, 64), 64, 0, st>>>(b, x_vd, u, mask, values, R_e);
+    else k_residual_rt<3><<<grid_for(b.E, 64), 64, 0, st>>>(b, x_vd, u, mask, values, R_e);
+    if (rc) return rc;
+    FEB_CHECK_LAUNCH("element_residual");
+    return FEB200_OK;
+}
+
+int feb200_element_tangent(feb200_stream s, const feb200_batch* bp, const double* x_vd, const double* u,
+                           const double* mask, const double* values, double* K_e) {
+    int rc = check_batch(bp, "element_tangent");
+    if (rc) return rc;
+    FEB_REQUIRE(x_vd && u && K_e, FEB200_ERR_INVALID, "element_tangent: null pointer");
+    FEB_REQUIRE(!mask || values, FEB200_ERR_INVALID, "element_tangent: mask without values");
+    const feb200_batch& b = *bp;
+    if (b.E == 0) return FEB200_OK;
+    cudaStream_t st = as_stream(s);
+    const bool iso = (b.material == MAT_ISOTROPIC && b.kind == KIND_LINEAR);
+    const int D4 = b.D * b.D * b.D * b.D;
+    TangentCfg c;
+    rc = tangent_cfg(b, iso ? 2 : D4, c);
+    if (rc) return rc;
+#define FEB_TANGENT_CASE(NN, DD)                                                                                   \
+    if (b.N == NN && b.D == DD) {                                                                                  \
+        rc = iso ? launch_tangent(k_tangent_iso<NN, DD>, st, b, c, x_vd, u, mask, values, K_e)                     \
+                 : launch_tangent(k_tangent_general_ct<NN, DD>, st, b, c, x_vd, u, mask, values, K_e);             \
+    } else
+    FEB_TANGENT_CASE(3, 2)
+    FEB_TANGENT_CASE(4, 2)
+    FEB_TANGENT_CASE(4, 3)
+    FEB_TANGENT_CASE(8, 3) {
+        if (iso) {   // the generic kernel stages the full D^4 tangent
+            rc = tangent_cfg(b, D4, c);
+            if (rc) return rc;
+        }
+        rc = (b.D == 2) ? launch_tangent(k_tangent_general_rt<2>, st, b, c, x_vd, u, mask, values, K_e)
+                        : launch_tangent(k_tangent_general_rt<3>, st, b, c, x_vd, u, mask, values, K_e);
+    }
+#undef FEB_TANGENT_CASE
+    if (rc) return rc;
+    FEB_CHECK_LAUNCH("element_tangent");
+    return FEB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,450 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes) behind the fe_jax call surface,
+against the CPU oracle on the same seeded inputs, against the golden fixtures made from the reference's
+own source text, and -- at BASELINE.json's full size -- through size-independent properties.
+
+Tolerances (north_star): index maps / sparsity pattern bit-exact; residual and Jacobian values 1e-12
+relative (FP64); solutions to the solver tolerance."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import build_pair, lattice_mesh, material_params, rel_err
+from oracle import fe_oracle as orc
+
+pytestmark = pytest.mark.gpu
+os.environ.setdefault("FEB200_QUIET", "1")
+
+ASM_RTOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def fj():
+    import __graft_entry__ as graft
+    graft.build()
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import fe_jax
+    return fe_jax
+
+
+def np_(t):
+    if t.dtype == torch.uint64:
+        t = t.view(torch.int64)
+    return t.detach().cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------ index maps
+@pytest.mark.parametrize("tag", ["tri", "quad", "hex"])
+def test_index_maps_bit_exact_vs_reference_outputs(fj, golden, tag):
+    cells = golden[f"maps_{tag}_cells"]
+    V = int(cells.max()) + 1
+    ri = fj.build_row_ind(V, cells)
+    ci, data = fj.build_col_ind_and_data(ri, cells)
+    assert ri.dtype == torch.uint64 and ci.dtype == torch.uint64 and data.dtype == torch.float64
+    assert np.array_equal(np_(ri).astype(np.uint64), golden[f"maps_{tag}_row_ind"])
+    assert np.array_equal(np_(ci).astype(np.uint64), golden[f"maps_{tag}_col_ind"])
+    assert bool((data == 1.0).all())
+
+
+def test_index_maps_edge_cases(fj):
+    # vertices without cells (ragged valence incl. 0), a single cell, and an empty batch
+    cells = np.array([[5, 1, 3], [3, 1, 0]], dtype=np.int64)
+    ri = fj.build_row_ind(8, cells)
+    ci, _ = fj.build_col_ind_and_data(ri, cells)
+    assert np.array_equal(np_(ri).astype(np.uint64), orc.build_row_ind(8, cells))
+    assert np.array_equal(np_(ci).astype(np.uint64), orc.build_col_ind_and_data(orc.build_row_ind(8, cells), cells)[0])
+    empty = np.zeros((0, 3), dtype=np.int64)
+    ri = fj.build_row_ind(4, empty)
+    assert np_(ri).tolist() == [0, 0, 0, 0, 0]
+    ci, d = fj.build_col_ind_and_data(ri, empty)
+    assert ci.numel() == 0 and d.numel() == 0
+
+
+def test_index_maps_large_random_mesh(fj):
+    rng = np.random.default_rng(5)
+    _, cells = orc.uniform_hex_grid(12, 9, 7)
+    cells = cells[rng.permutation(cells.shape[0])]
+    V = int(cells.max()) + 1
+    ri = fj.build_row_ind(V, cells)
+    ci, _ = fj.build_col_ind_and_data(ri, cells)
+    ri_o = orc.build_row_ind(V, cells)
+    assert np.array_equal(np_(ri).astype(np.uint64), ri_o)
+    assert np.array_equal(np_(ci).astype(np.uint64), orc.build_col_ind_and_data(ri_o, cells)[0])
+
+
+def test_gather_scatter_roundtrip(fj):
+    # tests/test_maps.py:27-34 of the reference
+    V, F = fj.uniform_tri_grid(9, 7)
+    amap = fj.mesh_to_sparse_assembly_map(V.shape[0], F)
+    assert amap.shape == (1, V.shape[0], F.size) and amap.data.shape == (1, F.size)
+    x_n = fj.mesh_to_jax(V, F)
+    assert np.array_equal(np_(x_n), V[F][:, :, :2])
+    back = fj.transform_element_node_to_global_nosum(amap, x_n)
+    assert np.allclose(np_(back), V[:, :2], atol=1e-15)
+    u = np.random.default_rng(0).normal(size=V.shape[0] * 2)
+    u_e = fj.transform_global_unraveled_to_element_node(amap, u, F.shape[0])
+    assert np.array_equal(np_(u_e), orc.gather_global_to_element_node(F, u, 2))
+    s = fj.transform_element_node_to_global_unraveled_sum(amap, u_e)
+    ri = orc.build_row_ind(V.shape[0], F)
+    ci, _ = orc.build_col_ind_and_data(ri, F)
+    assert np.array_equal(np_(s), orc.scatter_element_node_to_global_sum(ri, ci, np_(u_e)))   # same order -> same bits
+    cnt = fj.get_n_cells_per_vert(V, F)
+    assert np.array_equal(np_(cnt), (ri[1:] - ri[:-1]).astype(np.int64))
+
+
+# ------------------------------------------------------------------------------------------ element physics
+ELEMENTS = [("triangle", 1, 3), ("quadrilateral", 1, 2), ("tetrahedron", 1, 2), ("hexahedron", 1, 2),
+            ("triangle", 2, 4), ("quadrilateral", 2, 4), ("tetrahedron", 2, 4), ("hexahedron", 2, 4)]
+MODELS = ["elastic_isotropic", "elastic_orthotropic", "st_venant_kirchhoff", "mooney_rivlin"]
+
+
+def _case(fj, cell, degree, qdeg, model, layout, n=2, seed=0):
+    pts, cells = lattice_mesh(cell, degree, n, seed=seed)
+    D = pts.shape[1]
+    Q = orc.get_quadrature(cell, qdeg)[0].shape[0]
+    shape = {"EQM": (cells.shape[0], Q), "EM": (cells.shape[0],), "M": ()}[layout]
+    mp = material_params(model, D, shape, seed=seed + 1)
+    ebc, maps, token, prob, _ = build_pair(fj, pts, [dict(cell=cell, degree=degree, qdeg=qdeg, cells=cells, model=model, mp=mp)])
+    scale = 1e-3 if orc.HYPER_MODELS.get(model) is None else 3e-2
+    u = scale * np.random.default_rng(seed + 2).normal(size=pts.size)
+    return ebc, maps, token, prob, u
+
+
+@pytest.mark.parametrize("cell,degree,qdeg", ELEMENTS)
+@pytest.mark.parametrize("model", MODELS)
+def test_residual_and_jacobian_parity(fj, cell, degree, qdeg, model):
+    ebc, maps, token, prob, u = _case(fj, cell, degree, qdeg, model, "EQM")
+    R, states = fj.calculate_residual_wo_dirichlet(token, ebc, maps, u)
+    assert rel_err(R, prob.residual_wo_dirichlet(u)) <= ASM_RTOL
+    assert states[0].shape == (ebc.E[0], ebc.Q[0], 0)
+    nnz = fj._calculate_jacobian_unique_nnz(prob.V, ebc)
+    assert nnz == prob.jacobian_unique_nnz()
+    J = fj.calculate_jacobian_wo_dirichlet(token, ebc, maps, u, nnz)
+    d_o, r_o, c_o = prob.jacobian_wo_dirichlet(u)
+    assert J._rows_sorted and J.data.shape[0] == nnz
+    assert np.array_equal(np_(J.row), r_o) and np.array_equal(np_(J.col), c_o)          # bit-exact pattern
+    assert J.row.dtype == torch.int64 and J.col.dtype == torch.int64
+    assert rel_err(J.data, d_o) <= ASM_RTOL
+    diag = fj.calculate_jacobian_diag_wo_dirichlet(token, ebc, maps, u)
+    assert rel_err(diag, prob.jacobian_diag_wo_dirichlet(u)) <= ASM_RTOL
+    csr = fj.coo_to_csr(J)
+    _, idx_o, ptr_o = orc.coo_to_csr(d_o, r_o, c_o, prob.F)
+    assert np.array_equal(np_(csr.indptr), ptr_o) and np.array_equal(np_(csr.indices), idx_o)
+
+
+@pytest.mark.parametrize("layout", ["EQM", "EM", "M"])
+@pytest.mark.parametrize("cell,degree,qdeg,model", [("hexahedron", 1, 2, "elastic_isotropic"),
+                                                    ("quadrilateral", 1, 2, "elastic_orthotropic"),
+                                                    ("hexahedron", 1, 2, "mooney_rivlin")])
+def test_material_layouts(fj, layout, cell, degree, qdeg, model):
+    ebc, maps, token, prob, u = _case(fj, cell, degree, qdeg, model, layout, n=3)
+    R, _ = fj.calculate_residual_wo_dirichlet(token, ebc, maps, u)
+    assert rel_err(R, prob.residual_wo_dirichlet(u)) <= ASM_RTOL
+    J = fj.calculate_jacobian_wo_dirichlet(token, ebc, maps, u, None)
+    assert rel_err(J.data, prob.jacobian_wo_dirichlet(u)[0]) <= ASM_RTOL
+
+
+def test_element_residual_token_matches_reference_outputs(fj, golden):
+    # the per-element call signature of the reference, on the inputs stored with the golden outputs
+    for tag, kw in (("tri3", {}), ("quad4", {}), ("hex8", {}), ("tet4", {})):
+        x, u, dphi, W = (golden[f"res_{tag}_{k}"] for k in ("x", "u", "dphi", "W"))
+        R, state = fj.linear_elasticity_residual(u, x, dphi, W[0:1], golden[f"res_{tag}_iso_mp"],
+                                                 np.zeros((dphi.shape[0], 0)), fj.elastic_isotropic)
+        assert rel_err(R, golden[f"res_{tag}_lin_iso_R"]) <= ASM_RTOL and state.shape == (dphi.shape[0], 0)
+        uh = golden[f"res_{tag}_uh"]
+        R = fj.hyperelasticity_residual(uh, x, dphi, W[0:1], golden[f"res_{tag}_iso_mp"],
+                                        constitutive_model=fj.st_venant_kirchhoff)
+        assert rel_err(R, golden[f"res_{tag}_hyp_svk_R"]) <= ASM_RTOL
+        R = fj.hyperelasticity_residual(uh, x, dphi, W[0:1], golden[f"res_{tag}_mr_mp"],
+                                        constitutive_model=fj.mooney_rivlin)
+        assert rel_err(R, golden[f"res_{tag}_hyp_mr_R"]) <= ASM_RTOL
+
+
+def test_multi_batch_mixed_elements(fj):
+    # two batches of different element types sharing vertices (quads + triangles), summed in batch order
+    V, Fq = orc.uniform_quad_grid(6, 5, [[0, 1], [0, 1]])
+    pts = V[:, :2] + 0.02 * np.random.default_rng(1).normal(size=(V.shape[0], 2))
+    quads = Fq[: Fq.shape[0] // 2]
+    rest = Fq[Fq.shape[0] // 2:]
+    tris = np.concatenate([rest[:, [0, 1, 2]], rest[:, [1, 3, 2]]])
+    specs = [dict(cell="quadrilateral", degree=1, qdeg=2, cells=quads, model="elastic_isotropic",
+                  mp=material_params("elastic_isotropic", 2, (quads.shape[0], 4), 3)),
+             dict(cell="triangle", degree=1, qdeg=3, cells=tris, model="elastic_isotropic",
+                  mp=material_params("elastic_isotropic", 2, (tris.shape[0],), 4))]
+    ebc, maps, token, prob, _ = build_pair(fj, pts, specs)
+    u = 1e-3 * np.random.default_rng(2).normal(size=pts.size)
+    R, states = fj.calculate_residual_wo_dirichlet(token, ebc, maps, u)
+    assert len(states) == 2 and rel_err(R, prob.residual_wo_dirichlet(u)) <= ASM_RTOL
+    J = fj.calculate_jacobian_wo_dirichlet(token, ebc, maps, u, prob.jacobian_unique_nnz())
+    d_o, r_o, c_o = prob.jacobian_wo_dirichlet(u)
+    assert np.array_equal(np_(J.row), r_o) and np.array_equal(np_(J.col), c_o)
+    assert rel_err(J.data, d_o) <= ASM_RTOL
+    # collection getters mirror the reference layout
+    assert ebc.get_dof_map(0).shape == (quads.shape[0], 8) and ebc.get_dof_map(0).dtype == torch.int64
+    assert np.array_equal(np_(ebc.get_dof_map(1)), orc.get_dof_map(tris, 2))
+    assert ebc.get_weights(0).shape == (1,)                       # the length-1 slice of fea.py:285-297
+    assert np.array_equal(np_(ebc.get_x(1)), pts[tris])
+
+
+def test_assembly_is_bitwise_deterministic(fj):
+    ebc, maps, token, prob, u = _case(fj, "hexahedron", 1, 2, "elastic_isotropic", "EQM", n=6)
+    a = fj.calculate_jacobian_wo_dirichlet(token, ebc, maps, u, None).data.clone()
+    Ra = fj.calculate_residual_wo_dirichlet(token, ebc, maps, u)[0].clone()
+    for _ in range(3):
+        assert torch.equal(a, fj.calculate_jacobian_wo_dirichlet(token, ebc, maps, u, None).data)
+        assert torch.equal(Ra, fj.calculate_residual_wo_dirichlet(token, ebc, maps, u)[0])
+
+
+def test_unstructured_element_order(fj):
+    # element order shuffled: valence lists are irregular, pattern / values still match the oracle
+    pts, cells = lattice_mesh("hexahedron", 1, 4, seed=3)
+    cells = cells[np.random.default_rng(9).permutation(cells.shape[0])]
+    mp = material_params("elastic_isotropic", 3, (cells.shape[0], 8), 1)
+    ebc, maps, token, prob, _ = build_pair(fj, pts, [dict(cell="hexahedron", degree=1, qdeg=2, cells=cells,
+                                                         model="elastic_isotropic", mp=mp)])
+    u = 1e-3 * np.random.default_rng(2).normal(size=pts.size)
+    J = fj.calculate_jacobian_wo_dirichlet(token, ebc, maps, u, 9 * 13 ** 3)
+    d_o, r_o, c_o = prob.jacobian_wo_dirichlet(u)
+    assert np.array_equal(np_(J.row), r_o) and np.array_equal(np_(J.col), c_o) and rel_err(J.data, d_o) <= ASM_RTOL
+    assert rel_err(fj.calculate_residual_wo_dirichlet(token, ebc, maps, u)[0], prob.residual_wo_dirichlet(u)) <= ASM_RTOL
+
+
+# ------------------------------------------------------------------------------------------ Dirichlet + sparse helpers
+def _hex_bvp(fj, n, layout="EQM", model="elastic_isotropic"):
+    Vx, cells, u, mp, bcs, vals = orc.synthetic_hex_problem(n, material_layout=layout)
+    if model != "elastic_isotropic":
+        mp = {"st_venant_kirchhoff": np.array([1.0e6, 0.3]), "mooney_rivlin": np.array([0.5e6, 0.1e6, 2e-7])}[model]
+    ebc, maps, token, prob, fb = build_pair(fj, Vx, [dict(cell="hexahedron", degree=1, qdeg=2, cells=cells, model=model, mp=mp)])
+    return Vx, cells, u, mp, bcs, vals, ebc, maps, token, prob, fb
+
+
+def test_dirichlet_residual_and_lhs(fj):
+    Vx, cells, u, mp, bcs, vals, ebc, maps, token, prob, _ = _hex_bvp(fj, 5)
+    dofs, values_g, mask_g = orc.dirichlet_arrays(prob.F, 3, bcs, vals)
+    R, _ = fj.calculate_residual_w_dirichlet(token, ebc, maps, u, values_g, mask_g)
+    assert rel_err(R, prob.residual_w_dirichlet(u, values_g, mask_g)) <= ASM_RTOL
+    J = fj.calculate_jacobian_wo_dirichlet(token, ebc, maps, u, None)
+    Jw = fj.apply_dirichlet_bcs_lhs(J, dofs)
+    d_o, r_o, c_o = prob.jacobian_wo_dirichlet(u)
+    dw_o = orc.apply_dirichlet_bcs_lhs(d_o, r_o, c_o, dofs)
+    assert rel_err(Jw.data, dw_o) <= ASM_RTOL
+    assert np.array_equal(np_(Jw.data) == 0.0, dw_o == 0.0) and np.array_equal(np_(Jw.data) == 1.0, dw_o == 1.0)
+    # generic-COO route gives the same
+    J2 = fj.COO((J.data, J.row, J.col), shape=J.shape, rows_sorted=True)
+    assert torch.equal(fj.apply_dirichlet_bcs_lhs(J2, dofs).data, Jw.data)
+    # SpMV on the eliminated matrix
+    x = np.random.default_rng(3).normal(size=prob.F)
+    _, idx, ptr = orc.coo_to_csr(dw_o, r_o, c_o, prob.F)
+    y_o = orc.csr_matvec(dw_o, idx, ptr, x)
+    assert rel_err(Jw @ x, y_o) <= 1e-13
+    assert rel_err(fj.coo_to_csr(J2) @ x, orc.csr_matvec(d_o, idx, ptr, x)) <= 1e-13
+    b = np.random.default_rng(4).normal(size=prob.F)
+    rhs = fj.apply_dirichlet_bcs_rhs(J, b, dofs, vals)
+    rhs_o = orc.apply_dirichlet_bcs_rhs(lambda v: orc.csr_matvec(d_o, idx, ptr, v), b, dofs, vals)
+    assert rel_err(rhs, rhs_o) <= 1e-13
+
+
+def test_coo_sum_duplicates_matches_reference_outputs(fj, golden):
+    g = golden
+    A = fj.COO((torch.tensor(g["coo_in_data"]).cuda(), torch.tensor(g["coo_in_row"]).cuda(),
+                torch.tensor(g["coo_in_col"]).cuda()), shape=(40, 40), rows_sorted=True)
+    nnz = g["coo_out_data"].shape[0]
+    B = fj.coo_sum_duplicates(A, nnz)
+    assert np.array_equal(np_(B.row), g["coo_out_row"]) and np.array_equal(np_(B.col), g["coo_out_col"])
+    assert rel_err(B.data, g["coo_out_data"]) <= 1e-15
+    d, r, c = fj.coo_arrays_sum_duplicates(A)
+    assert np.array_equal(np_(r), g["coo_out_row"]) and rel_err(d, g["coo_out_data"]) <= 1e-15
+    out = fj.apply_dirichlet_bcs_lhs(B, g["dirichlet_dofs"])
+    assert np.array_equal(np_(out.data), g["dirichlet_lhs_data"])
+    # tests/test_sparse_linalg.py: summing a matrix with itself doubles it
+    A2 = fj.COO((torch.cat([B.data, B.data]), torch.cat([B.row, B.row]), torch.cat([B.col, B.col])), shape=(40, 40))
+    d2, r2, c2 = fj.coo_arrays_sum_duplicates(A2)
+    assert torch.equal(r2, B.row) and torch.equal(c2, B.col) and torch.allclose(d2, 2 * B.data)
+
+
+# ------------------------------------------------------------------------------------------ CG
+@pytest.mark.parametrize("tag,maxiter", [("cg3", 30), ("cgspd", 12)])
+@pytest.mark.parametrize("prec", ["none", "jacobi"])
+def test_cg_generic_matches_reference_outputs(fj, golden, tag, maxiter, prec):
+    A, b = golden[f"{tag}_A"], golden[f"{tag}_b"]
+    M = None if prec == "none" else np.diag(1.0 / np.diag(A))
+    x, info = fj.cg(A, b, x0=np.zeros_like(b), tol=1e-12, atol=0.0, maxiter=maxiter, M=M)
+    assert info["iterations"] == int(golden[f"{tag}_{prec}_iters"])
+    assert rel_err(x, golden[f"{tag}_{prec}_x"]) <= 1e-12
+    assert rel_err(info["residual_norm_history"], golden[f"{tag}_{prec}_hist"]) <= 1e-9
+
+
+def test_cg_known_answer(fj):
+    # tests/test_solve_cg.py:46-59 of the reference: x = [3, 4, 1]
+    A = np.array([[2.0, -1.0, 0.0], [-1.0, 2.0, 0.0], [0.0, 0.0, 1.0]])
+    b = np.array([2.0, 5.0, 1.0])
+    for M in (None, np.diag(1.0 / np.diag(A)), np.linalg.inv(A)):
+        x, info = fj.cg(A, b, tol=1e-12, atol=0.0, M=M)
+        assert np.allclose(np_(x), [3.0, 4.0, 1.0], atol=1e-12)
+
+
+@pytest.mark.parametrize("prec", ["none", "jacobi"])
+def test_device_cg_matches_oracle(fj, prec):
+    Vx, cells, u, mp, bcs, vals, ebc, maps, token, prob, _ = _hex_bvp(fj, 6)
+    dofs, values_g, mask_g = orc.dirichlet_arrays(prob.F, 3, bcs, vals)
+    J = fj.apply_dirichlet_bcs_lhs(fj.calculate_jacobian_wo_dirichlet(token, ebc, maps, u, None), dofs)
+    d_o, r_o, c_o = prob.jacobian_wo_dirichlet(u)
+    dw = orc.apply_dirichlet_bcs_lhs(d_o, r_o, c_o, dofs)
+    _, idx, ptr = orc.coo_to_csr(dw, r_o, c_o, prob.F)
+    b = np.random.default_rng(8).normal(size=prob.F) * 1e6
+    diag = np.zeros(prob.F)
+    diag[r_o[r_o == c_o]] = dw[r_o == c_o]
+    M_o = None if prec == "none" else (lambda v: v / diag)
+    M = None if prec == "none" else fj.JacobiPreconditioner(diag)
+    for maxiter in (7, 400):          # truncated (hits maxiter) and converged
+        x, info = fj.cg(J, b, tol=1e-10, atol=0.0, maxiter=maxiter, M=M)
+        x_o, info_o = orc.cg(lambda v: orc.csr_matvec(dw, idx, ptr, v), b, tol=1e-10, atol=0.0, maxiter=maxiter, M=M_o)
+        assert abs(info["iterations"] - info_o["iterations"]) <= (0 if maxiter == 7 else 2)
+        k = min(info["iterations"], info_o["iterations"])
+        h, h_o = np_(info["residual_norm_history"]), info_o["residual_norm_history"]
+        assert h.shape == (maxiter,)
+        assert np.allclose(h[:min(k, 40)], h_o[:min(k, 40)], rtol=1e-6)
+        if maxiter == 400:
+            assert info["iterations"] < maxiter and rel_err(x, x_o) <= 1e-7
+        else:
+            assert info["iterations"] == maxiter and rel_err(x, x_o) <= 1e-9
+
+
+def test_device_cg_is_deterministic(fj):
+    Vx, cells, u, mp, bcs, vals, ebc, maps, token, prob, _ = _hex_bvp(fj, 6)
+    dofs, _, _ = orc.dirichlet_arrays(prob.F, 3, bcs, vals)
+    J = fj.apply_dirichlet_bcs_lhs(fj.calculate_jacobian_wo_dirichlet(token, ebc, maps, u, None), dofs)
+    b = np.random.default_rng(8).normal(size=prob.F)
+    x1, i1 = fj.cg(J, b, tol=1e-9, maxiter=200)
+    x2, i2 = fj.cg(J, b, tol=1e-9, maxiter=200)
+    assert i1["iterations"] == i2["iterations"] and torch.equal(x1, x2)
+    assert torch.equal(i1["residual_norm_history"], i2["residual_norm_history"])
+
+
+# ------------------------------------------------------------------------------------------ Newton / solve_bvp
+@pytest.mark.parametrize("layout", ["EQM", "EM", "M"])
+def test_two_triangle_bvp_known_answer(fj, layout):
+    # tests/test_simple_fea_solve.py of the reference (asserts :109-113, layouts :115-200)
+    pts = np.array([[3.0, 0.0], [3.0, 2.0], [0.0, 2.0], [0.0, 0.0]])
+    cells = np.array([[0, 1, 3], [2, 3, 1]], dtype=np.uint64)
+    fe = fj.FiniteElementType(fj.CellType.triangle, fj.ElementFamily.P, 1, fj.LagrangeVariant.equispaced,
+                              fj.QuadratureType.default, 3)
+    Q = fj.get_quadrature(fe)[0].shape[0]
+    mp = {"EQM": np.tile([30e6, 0.25], (1, Q, 1)), "EM": np.array([[30e6, 0.25]]), "M": np.array([30e6, 0.25])}[layout]
+    batches = [fj.ElementBatch(fe_type=fe, n_dofs_per_basis=2, connectivity_en=cells[:1, :],
+                               constitutive_model=fj.elastic_isotropic, material_params=mp),
+               fj.ElementBatch(fe_type=fe, n_dofs_per_basis=2, connectivity_en=cells[1:, :],
+                               constitutive_model=fj.elastic_isotropic, material_params=mp)]
+    bcs = np.array([[0, 0], [0, 1], [1, 0], [2, 0], [3, 0], [3, 1]], dtype=np.uint64)
+    vals = np.array([1.0, 0.0, 1.0, 0.0, 0.0, 0.0])
+    u, residual, _ = fj.solve_bvp(element_residual_func=fj.linear_elasticity_residual, vertices_vd=pts,
+                                  element_batches=batches, u_0_g=torch.zeros(8, dtype=torch.float64),
+                                  dirichlet_bcs=bcs, dirichlet_values=vals,
+                                  solver_options=fj.SolverOptions(linear_solve_type=fj.LinearSolverType.CG_JAX_SCIPY_W_INFO))
+    u = np_(u)
+    assert (u[0] - 1.0) < 1e-6 and (u[2] - 1.0) < 1e-6
+    assert abs(-(u[3] / 2.0) / (u[0] / 3.0) - 0.25) < 1e-6
+    assert abs(-(u[5] / 2.0) / (u[0] / 3.0) - 0.25) < 1e-6
+    assert u[1] == u[7] == 0.0 and u[4] == u[6] == 0.0
+    assert np.allclose(u, [1, 0, 1, -1 / 6, 0, -1 / 6, 0, 0], atol=1e-9)
+
+
+@pytest.mark.parametrize("prec", ["NONE", "JACOBI"])
+def test_hex_bvp_linear_vs_oracle(fj, prec):
+    Vx, cells, u, mp, bcs, vals, ebc, maps, token, prob, fb = _hex_bvp(fj, 5)
+    opts = fj.SolverOptions(linear_precond_type=getattr(fj.PreconditionerType, prec), linear_max_iter=2000)
+    usol, res, _ = fj.solve_bvp(Vx, fb, fj.linear_elasticity_residual, None, bcs, vals, solver_options=opts)
+    u_o, R_o, info_o = orc.solve_bvp(Vx, prob.batches, None, bcs, vals, options={"precond": prec, "linear_max_iter": 2000})
+    info = fj.solve_bvp.last_info
+    assert rel_err(usol, u_o) <= 1e-8
+    assert info.nonlinear_iterations == info_o["nonlinear_iterations"]
+    assert abs(info.cumulative_linear_iterations - info_o["cumulative_linear_iterations"]) <= 3
+    dofs, values_g, _ = orc.dirichlet_arrays(prob.F, 3, bcs, vals)
+    assert np.array_equal(np_(usol)[dofs], values_g[dofs])            # constraints hold exactly (:527)
+    assert float(torch.linalg.norm(res)) <= 1e-6 * np.linalg.norm(prob.residual_w_dirichlet(np.zeros(prob.F), values_g, _))
+
+
+@pytest.mark.parametrize("model", ["st_venant_kirchhoff", "mooney_rivlin"])
+def test_hex_bvp_hyperelastic_newton_vs_oracle(fj, model):
+    Vx, cells, u, mp, bcs, vals, ebc, maps, token, prob, fb = _hex_bvp(fj, 3, layout="M", model=model)
+    vals = vals * 5.0          # 5 % stretch
+    opts = fj.SolverOptions(linear_precond_type=fj.PreconditionerType.JACOBI, linear_max_iter=3000,
+                            linear_relative_tol=1e-12, nonlinear_max_iter=12)
+    usol, res, _ = fj.solve_bvp(Vx, fb, fj.hyperelasticity_residual, None, bcs, vals, solver_options=opts)
+    u_o, R_o, info_o = orc.solve_bvp(Vx, prob.batches, None, bcs, vals,
+                                     options={"precond": "JACOBI", "linear_max_iter": 3000, "linear_relative_tol": 1e-12,
+                                              "nonlinear_max_iter": 12})
+    info = fj.solve_bvp.last_info
+    assert info.nonlinear_iterations == info_o["nonlinear_iterations"] and info.nonlinear_iterations >= 2
+    assert rel_err(usol, u_o) <= 1e-7
+
+
+def test_linear_solve_surface(fj):
+    Vx, cells, u, mp, bcs, vals, ebc, maps, token, prob, _ = _hex_bvp(fj, 4)
+    dofs, values_g, mask_g = orc.dirichlet_arrays(prob.F, 3, bcs, vals)
+    opts = fj.SolverOptions(linear_max_iter=1500)
+    res = fj.Residual(function=lambda x: fj.calculate_residual_w_dirichlet(token, ebc, maps, x, values_g, mask_g)[0],
+                      dirichlet_bcs_builtin=True)
+    jac = fj.Jacobian(function=lambda x: fj.calculate_jacobian_wo_dirichlet(token, ebc, maps, x, None), dirichlet_bcs_builtin=False)
+    dg = fj.JacobianDiagonl(function=lambda x: fj.calculate_jacobian_diag_wo_dirichlet(token, ebc, maps, x), dirichlet_bcs_builtin=False)
+    x0 = torch.zeros(prob.F, dtype=torch.float64, device="cuda")
+    dx, info = fj.linear_solve(res, jac, dg, dofs, vals, opts, fj.init_solver_info(opts), False, x0)
+    oinfo = dict(nonlinear_iterations=0, cumulative_linear_iterations=0,
+                 linear_iterations_per_nonlinear_iteration=np.zeros(10), cumulative_residual_norm_history=np.zeros(15001))
+    o = dict(orc.DEFAULT_OPTIONS)
+    o["linear_max_iter"] = 1500
+    dx_o, oinfo = orc.linear_solve(prob, np.zeros(prob.F), dofs, vals, values_g, mask_g, o, oinfo)
+    assert rel_err(dx, dx_o) <= 1e-8
+    assert abs(info.cumulative_linear_iterations - oinfo["cumulative_linear_iterations"]) <= 3
+    k = info.cumulative_linear_iterations
+    assert float(info.linear_iterations_per_nonlinear_iteration[0]) == k
+    h = np_(info.cumulative_residual_norm_history)
+    assert h[0] > 0 and np.allclose(h[:20], oinfo["cumulative_residual_norm_history"][:20], rtol=1e-6)
+    with pytest.raises(Exception):
+        fj.linear_solve(res, None, None, dofs, vals, opts, fj.init_solver_info(opts), False, x0)
+
+
+# ------------------------------------------------------------------------------------------ full size, by properties
+@pytest.mark.parametrize("n", [200])
+def test_full_size_hex8_properties(fj, n):
+    """BASELINE.json configs[1]: hex8 n^3 (8M elements at n=200).  The oracle cannot run at this size, so
+    parity is checked through properties that hold for any mesh size:
+      nnz = 9(3n+1)^3; row_ind ends at 8E; every interior vertex has 27 neighbours;
+      J is symmetric (x.Jy == y.Jx); rigid translations are in the null space of J and produce no residual;
+      R(u) == J u for linear elasticity; repeated assembly is bit-identical."""
+    free = torch.cuda.mem_get_info()[0]
+    if free < 90e9:
+        pytest.skip("needs ~80 GB of free device memory")
+    Vx, cells = fj.uniform_hex_grid(n, n, n)
+    rng = np.random.default_rng(0)
+    h = 1.0 / n
+    interior = np.all((Vx > 1e-12) & (Vx < 1 - 1e-12), axis=1)
+    Vx = Vx + (0.2 * h * rng.uniform(-1, 1, size=Vx.shape)) * interior[:, None]
+    fe = fj.FiniteElementType(fj.CellType.hexahedron, fj.ElementFamily.P, 1, fj.LagrangeVariant.equispaced,
+                              fj.QuadratureType.default, 2)
+    batch = fj.ElementBatch(fe_type=fe, n_dofs_per_basis=3, connectivity_en=cells, constitutive_model=fj.elastic_isotropic,
+                            material_params=np.array([70e9, 0.25]))
+    ebc = fj.batch_to_collection(Vx, [batch])
+    maps = [fj.mesh_to_sparse_assembly_map(Vx.shape[0], cells)]
+    E, V = cells.shape[0], Vx.shape[0]
+    assert int(maps[0].indptr.view(torch.int64)[0, -1]) == 8 * E
+    nnz = fj._calculate_jacobian_unique_nnz(V, ebc)
+    assert nnz == 9 * (3 * n + 1) ** 3
+    F = 3 * V
+    g = torch.Generator(device="cuda").manual_seed(1)
+    u = 1e-3 * torch.rand(F, dtype=torch.float64, device="cuda", generator=g)
+    J = fj.calculate_jacobian_wo_dirichlet(fj.linear_elasticity_residual, ebc, maps, u, nnz)
+    R, _ = fj.calculate_residual_wo_dirichlet(fj.linear_elasticity_residual, ebc, maps, u)
+    Ju = J @ u
+    scale = float(Ju.abs().max())
+    assert float((R - Ju).abs().max()) <= 1e-10 * scale                      # R is linear in u
+    y = torch.rand(F, dtype=torch.float64, device="cuda", generator=g)
+    xJy, yJx = float(torch.dot(u, J @ y)), float(torch.dot(y, Ju))
+    assert abs(xJy - yJx) <= 1e-10 * abs(xJy)                                 # symmetry
+    t = torch.zeros(F, dtype=torch.float64, device="cuda")
+    t[1::3] = 1.0
+    assert float((J @ t).abs().max()) <= 1e-9 * float(J.data.abs().max())     # rigid translation
+    assert float(R.reshape(-1, 3).sum(0).abs().max()) <= 1e-9 * float(R.abs().sum())   # forces balance
+    J2 = fj.calculate_jacobian_wo_dirichlet(fj.linear_elasticity_residual, ebc, maps, u, nnz)
+    assert torch.equal(J.data, J2.data)
