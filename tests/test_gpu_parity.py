@@ -365,7 +365,10 @@ def test_hex_bvp_linear_vs_oracle(fj, prec):
     assert float(torch.linalg.norm(res)) <= 1e-6 * np.linalg.norm(prob.residual_w_dirichlet(np.zeros(prob.F), values_g, _))
 
 
-@pytest.mark.parametrize("model", ["st_venant_kirchhoff", "mooney_rivlin"])
+# mooney_rivlin is covered by the residual / Jacobian parity tests only: the reference's literal formula
+# (hyperelasticity.py:79-88) has a non-symmetric tangent and a stressed rest state, so CG on it breaks down
+# in the oracle as well (DESIGN.md "Out of scope / known reference behaviour").
+@pytest.mark.parametrize("model", ["st_venant_kirchhoff"])
 def test_hex_bvp_hyperelastic_newton_vs_oracle(fj, model):
     Vx, cells, u, mp, bcs, vals, ebc, maps, token, prob, fb = _hex_bvp(fj, 3, layout="M", model=model)
     vals = vals * 5.0          # 5 % stretch
@@ -403,6 +406,16 @@ def test_linear_solve_surface(fj):
     assert h[0] > 0 and np.allclose(h[:20], oinfo["cumulative_residual_norm_history"][:20], rtol=1e-6)
     with pytest.raises(Exception):
         fj.linear_solve(res, None, None, dofs, vals, opts, fj.init_solver_info(opts), False, x0)
+
+
+def test_mooney_rivlin_rest_state_is_the_reference_one(fj):
+    # at u = 0 the literal formula gives S = 4*C2*I, hence a non-zero residual on free faces
+    Vx, cells, u, mp, bcs, vals, ebc, maps, token, prob, fb = _hex_bvp(fj, 3, layout="M", model="mooney_rivlin")
+    R, _ = fj.calculate_residual_wo_dirichlet(token, ebc, maps, np.zeros(prob.F))
+    R_o = prob.residual_wo_dirichlet(np.zeros(prob.F))
+    assert rel_err(R, R_o) <= ASM_RTOL and float(R.abs().max()) > 1e3
+    interior = np.all((Vx > 1e-9) & (Vx < 1 - 1e-9), axis=1)
+    assert np.abs(np_(R).reshape(-1, 3)[interior]).max() <= 1e-9 * float(R.abs().max())   # constant stress: interior balance
 
 
 # ------------------------------------------------------------------------------------------ full size, by properties
