@@ -16,41 +16,118 @@
 
 namespace feb {
 
-// one warp per vertex; accumulators in shared memory: acc[r][i][j] for neighbour rank r
+// Final store of one vertex's row panel from the shared-memory accumulators (panel layout), with the
+// optional fused Dirichlet elimination (apply_dirichlet_bcs_lhs, sparse_matrix.py:157-184).
+template <int U>
+__device__ __forceinline__ void store_panel(int lane, int64_t a, int deg, int64_t p0, const double* acc,
+                                            double* __restrict__ values, int accumulate,
+                                            const int32_t* __restrict__ nindices, const double* __restrict__ mask) {
+    constexpr int U2 = U * U;
+    const int row_len = U * deg;
+    double* dst = values + (int64_t)U2 * p0;
+    for (int t = lane; t < U * row_len; t += 32) {
+        double v = acc[t];
+        if (accumulate) v += dst[t];
+        if (mask) {
+            const int i = t / row_len, c = t - i * row_len;
+            const int r = c / U, j = c - r * U;
+            const int64_t colv = nindices[p0 + r];
+            const bool rm = mask[a * U + i] != 0.0;
+            const bool cm = mask[colv * U + j] != 0.0;
+            if (rm || cm) v = (rm && colv == a && i == j) ? 1.0 : 0.0;
+        }
+        dst[t] = v;
+    }
+}
+
+// one warp per vertex; accumulators in shared memory in PANEL layout: acc[i*(U*deg) + U*r + j].
+// Generic variant: any N (chunk = N*U*U doubles per incident slot), slots processed one after the other.
 template <int U>
 __global__ void k_assemble_csr(const unsigned long long* __restrict__ row_ind, const unsigned long long* __restrict__ col_ind,
                                int64_t V, int N, const double* __restrict__ K_e, const uint16_t* __restrict__ slot_rank,
-                               const int64_t* __restrict__ nindptr, int max_deg, double* __restrict__ values, int accumulate) {
+                               const int64_t* __restrict__ nindptr, int max_deg, double* __restrict__ values, int accumulate,
+                               const int32_t* __restrict__ nindices, const double* __restrict__ mask) {
     constexpr int U2 = U * U;
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     double* acc = smem + (size_t)warp * max_deg * U2;
-    const int blk = N * U2;                                    // doubles per slot chunk
+    const int items = N * U;                                   // (block, row-of-block) items per slot chunk
     for (int64_t a = (int64_t)blockIdx.x * wpb + warp; a < V; a += (int64_t)gridDim.x * wpb) {
         const int64_t p0 = nindptr[a];
         const int deg = (int)(nindptr[a + 1] - p0);
+        const int row_len = U * deg;
         for (int t = lane; t < deg * U2; t += 32) acc[t] = 0.0;
         __syncwarp();
         const unsigned long long s0 = row_ind[a], s1 = row_ind[a + 1];
         for (unsigned long long k = s0; k < s1; ++k) {          // ascending slots == ascending elements
             const unsigned long long slot = col_ind[k];
-            const double* chunk = K_e + slot * (unsigned long long)blk;
+            const double* chunk = K_e + slot * (unsigned long long)(N * U2);
             const uint16_t* rk = slot_rank + slot * (unsigned long long)N;
-            for (int t = lane; t < blk; t += 32) {
-                const int bn = t / U2, c = t - bn * U2;
-                acc[(int)rk[bn] * U2 + c] += chunk[t];          // distinct bn -> distinct rank: no conflicts
+            for (int t = lane; t < items; t += 32) {
+                const int bn = t / U, i = t - bn * U;
+                double* dstp = acc + i * row_len + U * (int)rk[bn];   // distinct bn -> distinct rank: no conflicts
+#pragma unroll
+                for (int j = 0; j < U; ++j) dstp[j] += chunk[bn * U2 + i * U + j];
             }
             __syncwarp();
         }
-        // row panel: values[U2*p0 + i*(U*deg) + U*r + j] = acc[r][i][j]
+        store_panel<U>(lane, a, deg, p0, acc, values, accumulate, nindices, mask);
+        __syncwarp();
+    }
+}
+
+// Fast variant for N*U <= 32 (tri3, quad4, tet4, hex8): lane <-> (local node bn, block row i).  The chunks
+// of up to PD incident slots are loaded first (PD*U independent 8-byte loads in flight per lane), then
+// added in slot order.
+template <int U, int PD>
+__global__ void __launch_bounds__(256) k_assemble_csr_pre(const unsigned long long* __restrict__ row_ind,
+                                                          const unsigned long long* __restrict__ col_ind, int64_t V, int N,
+                                                          const double* __restrict__ K_e,
+                                                          const uint16_t* __restrict__ slot_rank,
+                                                          const int64_t* __restrict__ nindptr, int max_deg,
+                                                          double* __restrict__ values, int accumulate,
+                                                          const int32_t* __restrict__ nindices,
+                                                          const double* __restrict__ mask) {
+    constexpr int U2 = U * U;
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    double* acc = smem + (size_t)warp * max_deg * U2;
+    const int items = N * U;
+    const bool has_item = lane < items;
+    const int bn = lane / U, i = lane - bn * U;
+    for (int64_t a = (int64_t)blockIdx.x * wpb + warp; a < V; a += (int64_t)gridDim.x * wpb) {
+        const int64_t p0 = nindptr[a];
+        const int deg = (int)(nindptr[a + 1] - p0);
         const int row_len = U * deg;
-        double* dst = values + (int64_t)U2 * p0;
-        for (int t = lane; t < U * row_len; t += 32) {
-            const int i = t / row_len, c = t - i * row_len;
-            const int r = c / U, j = c - r * U;
-            const double v = acc[r * U2 + i * U + j];
-            dst[t] = accumulate ? dst[t] + v : v;
+        for (int t = lane; t < deg * U2; t += 32) acc[t] = 0.0;
+        const unsigned long long s0 = row_ind[a], s1 = row_ind[a + 1];
+        for (unsigned long long kb = s0; kb < s1; kb += PD) {
+            const int cnt = (int)((s1 - kb) < (unsigned long long)PD ? (s1 - kb) : PD);
+            const unsigned long long my_slot = (lane < cnt) ? col_ind[kb + lane] : 0ull;
+            double v[PD][U];
+            int rk[PD];
+#pragma unroll
+            for (int k = 0; k < PD; ++k) {
+                const unsigned long long slot = __shfl_sync(0xffffffffu, my_slot, k);
+                if (k < cnt && has_item) {
+                    const double* src = K_e + slot * (unsigned long long)(N * U2) + bn * U2 + i * U;
+#pragma unroll
+                    for (int j = 0; j < U; ++j) v[k][j] = __ldcs(src + j);          // streamed once
+                    rk[k] = (int)slot_rank[slot * (unsigned long long)N + bn];
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < PD; ++k) {
+                if (k < cnt && has_item) {
+                    double* dstp = acc + i * row_len + U * rk[k];
+#pragma unroll
+                    for (int j = 0; j < U; ++j) dstp[j] += v[k][j];
+                }
+                __syncwarp();
+            }
         }
+        store_panel<U>(lane, a, deg, p0, acc, values, accumulate, nindices, mask);
         __syncwarp();
     }
 }
@@ -148,9 +225,10 @@ extern "C" {
 
 int feb200_assemble_csr(feb200_stream s, const feb200_batch_map* map, int64_t V, int32_t U, const double* K_e,
                         const uint16_t* slot_rank, const int64_t* nindptr, int32_t max_deg, double* values,
-                        int32_t accumulate) {
+                        int32_t accumulate, const int32_t* nindices, const double* mask) {
     FEB_REQUIRE(map && map->row_ind && map->col_ind && K_e && slot_rank && nindptr && values, FEB200_ERR_INVALID,
                 "assemble_csr: null pointer");
+    FEB_REQUIRE(!mask || nindices, FEB200_ERR_INVALID, "assemble_csr: mask given without nindices");
     FEB_REQUIRE(max_deg > 0 && max_deg <= 65535, FEB200_ERR_INVALID, "assemble_csr: max_deg=%d out of range", max_deg);
     if (V == 0) return FEB200_OK;
     cudaStream_t st = as_stream(s);
@@ -164,11 +242,20 @@ int feb200_assemble_csr(feb200_stream s, const feb200_batch_map* map, int64_t V,
     int64_t g = ceil_div(V, wpb);
     const int64_t cap = (int64_t)sm_count() * 16;
     if (g > cap) g = cap;
+    const bool fast = (map->N * U <= 32);
 #define FEB_ASM(UU)                                                                                                    \
     {                                                                                                                  \
-        auto kern = k_assemble_csr<UU>;                                                                                \
-        if (smem > 48 * 1024) FEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        kern<<<(int)g, wpb * 32, smem, st>>>(ri, ci, V, map->N, K_e, slot_rank, nindptr, max_deg, values, accumulate);  \
+        if (fast) {                                                                                                    \
+            auto kern = k_assemble_csr_pre<UU, 8>;                                                                     \
+            if (smem > 48 * 1024) FEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            kern<<<(int)g, wpb * 32, smem, st>>>(ri, ci, V, map->N, K_e, slot_rank, nindptr, max_deg, values, accumulate, \
+                                                 nindices, mask);                                                      \
+        } else {                                                                                                       \
+            auto kern = k_assemble_csr<UU>;                                                                            \
+            if (smem > 48 * 1024) FEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            kern<<<(int)g, wpb * 32, smem, st>>>(ri, ci, V, map->N, K_e, slot_rank, nindptr, max_deg, values, accumulate, \
+                                                 nindices, mask);                                                      \
+        }                                                                                                              \
     }
     if (U == 2) FEB_ASM(2)
     else if (U == 3) FEB_ASM(3)

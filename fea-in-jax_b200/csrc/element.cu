@@ -179,57 +179,123 @@ __device__ __forceinline__ void stage_geometry(const feb200_batch& b, int N, int
     __syncthreads();
 }
 
-// isotropic linear elasticity, closed form:
+// isotropic linear elasticity, closed form, q outer with the whole block row K[a, 0..N) in registers:
 //   K_ab[d][k] = sum_q w (lam g_a[d] g_b[k] + mu g_a[k] g_b[d]) + delta_dk sum_q w mu g_a.g_b
-template <int N, int D>
-__global__ void k_tangent_iso(feb200_batch b, int epb, int per_el, const double* __restrict__ x_vd,
-                              const double* __restrict__ u, const double* __restrict__ mask,
-                              const double* __restrict__ values, double* __restrict__ K_e) {
-    constexpr int NU = N * D;
+// CONST_MAT (material constant over the element: layouts (M,) and (E,M)): accumulate
+//   S_ab[i][l] = sum_q w g_a[i] g_b[l]   (9 FMA per pair and point instead of 21)
+// and apply lam, mu once: K_ab[d][k] = lam S[d][k] + mu S[k][d] + delta_dk mu tr S.
+// The block row (N*D*D doubles, contiguous in K_e) is transposed through shared memory in PASSES
+// pieces so that the global stores are full 32-byte sectors written by consecutive lanes.
+template <int N, int D, bool CONST_MAT, int PASSES>
+__global__ void __launch_bounds__(128) k_tangent_iso(feb200_batch b, int epb, int per_el, const double* __restrict__ x_vd,
+                                                     const double* __restrict__ u, const double* __restrict__ mask,
+                                                     const double* __restrict__ values, double* __restrict__ K_e) {
+    constexpr int NU = N * D, D2 = D * D;
+    constexpr int NB = N / PASSES;                  // blocks per pass
+    constexpr int PIECE = NB * D2;                  // doubles per thread and pass
+    static_assert(N % PASSES == 0, "PASSES must divide N");
     extern __shared__ double smem[];
     double* s_dphi = smem;
-    double* s_el = smem + (size_t)b.Q * NU;
+    double* s_el = smem + (size_t)b.Q * NU;         // geometry staging, later reused as store staging
     for (int i = threadIdx.x; i < b.Q * NU; i += blockDim.x) s_dphi[i] = b.dphi[i];
     const int e_l = threadIdx.x / N, a = threadIdx.x - e_l * N;
     const int Q = b.Q;
+    const int n_slots_blk = epb * N;                // (element, node) slots handled per tile
     for (int64_t e0 = (int64_t)blockIdx.x * epb; e0 < b.E; e0 += (int64_t)gridDim.x * epb) {
         const int64_t e = e0 + e_l;
         const bool active = (e_l < epb) && (e < b.E);
         __syncthreads();
         stage_geometry<D>(b, N, e_l, a, e, active, x_vd, u, mask, values, s_dphi, s_el, per_el, 2, true);
-        if (!active) continue;
-        const double* g = s_el + (size_t)e_l * per_el + 2 * NU;
-        const double* wdet = g + (size_t)Q * NU;
-        const double* aux = wdet + Q;
-        double* out = K_e + ((e * N + a) * (int64_t)N) * (D * D);
-        for (int bn = 0; bn < N; ++bn) {
-            double acc[D][D];
-            double tr = 0.0;
+        double acc[N][D2];
 #pragma unroll
-            for (int d = 0; d < D; ++d)
+        for (int bn = 0; bn < N; ++bn)
 #pragma unroll
-                for (int k = 0; k < D; ++k) acc[d][k] = 0.0;
+            for (int c = 0; c < D2; ++c) acc[bn][c] = 0.0;
+        if (active) {
+            const double* g = s_el + (size_t)e_l * per_el + 2 * NU;
+            const double* wdet = g + (size_t)Q * NU;
+            const double* aux = wdet + Q;
             for (int q = 0; q < Q; ++q) {
-                const double w = wdet[q], wl = w * aux[q * 2], wm = w * aux[q * 2 + 1];
-                double ga[D], gb[D];
+                const double* gq = g + (size_t)q * NU;
+                const double w = wdet[q];
+                double ga[D];
 #pragma unroll
-                for (int d = 0; d < D; ++d) { ga[d] = g[(size_t)q * NU + a * D + d]; gb[d] = g[(size_t)q * NU + bn * D + d]; }
-                double dot = 0.0;
+                for (int d = 0; d < D; ++d) ga[d] = gq[a * D + d];
+                if (CONST_MAT) {
+                    double wga[D];
 #pragma unroll
-                for (int d = 0; d < D; ++d) dot += ga[d] * gb[d];
-                tr += wm * dot;
+                    for (int d = 0; d < D; ++d) wga[d] = w * ga[d];
 #pragma unroll
-                for (int d = 0; d < D; ++d)
+                    for (int bn = 0; bn < N; ++bn) {
+                        double gb[D];
 #pragma unroll
-                    for (int k = 0; k < D; ++k) acc[d][k] += wl * ga[d] * gb[k] + wm * ga[k] * gb[d];
+                        for (int d = 0; d < D; ++d) gb[d] = gq[bn * D + d];
+#pragma unroll
+                        for (int i = 0; i < D; ++i)
+#pragma unroll
+                            for (int l = 0; l < D; ++l) acc[bn][i * D + l] += wga[i] * gb[l];
+                    }
+                } else {
+                    const double wl = w * aux[q * 2], wm = w * aux[q * 2 + 1];
+                    double la[D], ma[D];
+#pragma unroll
+                    for (int d = 0; d < D; ++d) { la[d] = wl * ga[d]; ma[d] = wm * ga[d]; }
+#pragma unroll
+                    for (int bn = 0; bn < N; ++bn) {
+                        double gb[D];
+#pragma unroll
+                        for (int d = 0; d < D; ++d) gb[d] = gq[bn * D + d];
+                        double dot = 0.0;
+#pragma unroll
+                        for (int d = 0; d < D; ++d) dot += ma[d] * gb[d];
+#pragma unroll
+                        for (int d = 0; d < D; ++d)
+#pragma unroll
+                            for (int k = 0; k < D; ++k) acc[bn][d * D + k] += la[d] * gb[k] + ma[k] * gb[d];
+#pragma unroll
+                        for (int d = 0; d < D; ++d) acc[bn][d * D + d] += dot;
+                    }
+                }
             }
+            if (CONST_MAT) {
+                const double lam = aux[0], mu = aux[1];
 #pragma unroll
-            for (int d = 0; d < D; ++d) acc[d][d] += tr;
+                for (int bn = 0; bn < N; ++bn) {
+                    double S[D2];
+                    double tr = 0.0;
 #pragma unroll
-            for (int d = 0; d < D; ++d)
+                    for (int c = 0; c < D2; ++c) S[c] = acc[bn][c];
 #pragma unroll
-                for (int k = 0; k < D; ++k) out[bn * D * D + d * D + k] = acc[d][k];
+                    for (int d = 0; d < D; ++d) tr += S[d * D + d];
+#pragma unroll
+                    for (int d = 0; d < D; ++d)
+#pragma unroll
+                        for (int k = 0; k < D; ++k)
+                            acc[bn][d * D + k] = lam * S[d * D + k] + mu * S[k * D + d] + (d == k ? mu * tr : 0.0);
+                }
+            }
         }
+        // ---- coalesced store of the block rows through shared memory
+        const int64_t slot0 = e0 * N;                                            // first slot of this tile
+        const int64_t n_slots = ((b.E - e0) < epb ? (b.E - e0) : epb) * (int64_t)N;
+#pragma unroll
+        for (int pass = 0; pass < PASSES; ++pass) {
+            __syncthreads();                                                     // geometry / previous pass consumed
+            if (active) {
+                double* dst = s_el + (size_t)threadIdx.x * PIECE;
+#pragma unroll
+                for (int bn = 0; bn < NB; ++bn)
+#pragma unroll
+                    for (int c = 0; c < D2; ++c) dst[bn * D2 + c] = acc[pass * NB + bn][c];
+            }
+            __syncthreads();
+            for (int64_t i = threadIdx.x; i < n_slots * PIECE; i += blockDim.x) {
+                const int64_t t = i / PIECE;
+                const int c = (int)(i - t * PIECE);
+                K_e[(slot0 + t) * (int64_t)(N * D2) + pass * PIECE + c] = s_el[t * PIECE + c];
+            }
+        }
+        (void)n_slots_blk;
     }
 }
 
@@ -376,12 +442,13 @@ static int launch_residual_ct(cudaStream_t st, const feb200_batch& b, const doub
 }
 
 struct TangentCfg { int epb, per_el, threads; size_t smem; };
-static int tangent_cfg(const feb200_batch& b, int aux, TangentCfg& c) {
+static int tangent_cfg(const feb200_batch& b, int aux, TangentCfg& c, int max_threads = 256, int stage_doubles_per_thread = 0) {
     const int NU = b.N * b.D;
     c.per_el = 2 * NU + b.Q * NU + b.Q + b.Q * aux;
+    if (c.per_el < stage_doubles_per_thread * b.N) c.per_el = stage_doubles_per_thread * b.N;   // store staging aliases it
     const size_t table = (size_t)b.Q * NU * sizeof(double);
     const size_t budget = 96 * 1024;
-    int epb = 256 / b.N;
+    int epb = max_threads / b.N;
     while (epb > 1 && table + (size_t)epb * c.per_el * sizeof(double) > budget) --epb;
     if (epb < 1) epb = 1;
     c.epb = epb;
@@ -441,21 +508,27 @@ int feb200_element_tangent(feb200_stream s, const feb200_batch* bp, const double
     const bool iso = (b.material == MAT_ISOTROPIC && b.kind == KIND_LINEAR);
     const int D4 = b.D * b.D * b.D * b.D;
     TangentCfg c;
-    rc = tangent_cfg(b, iso ? 2 : D4, c);
-    if (rc) return rc;
-#define FEB_TANGENT_CASE(NN, DD)                                                                                   \
+    const bool cm = (b.layout != LAYOUT_EQM);
+    constexpr int PASSES_HEX = 2;
+#define FEB_TANGENT_CASE(NN, DD, PP)                                                                               \
     if (b.N == NN && b.D == DD) {                                                                                  \
-        rc = iso ? launch_tangent(k_tangent_iso<NN, DD>, st, b, c, x_vd, u, mask, values, K_e)                     \
-                 : launch_tangent(k_tangent_general_ct<NN, DD>, st, b, c, x_vd, u, mask, values, K_e);             \
+        if (iso) {                                                                                                 \
+            rc = tangent_cfg(b, 2, c, 128, (NN / PP) * DD * DD);                                                   \
+            if (rc) return rc;                                                                                     \
+            rc = cm ? launch_tangent(k_tangent_iso<NN, DD, true, PP>, st, b, c, x_vd, u, mask, values, K_e)        \
+                    : launch_tangent(k_tangent_iso<NN, DD, false, PP>, st, b, c, x_vd, u, mask, values, K_e);      \
+        } else {                                                                                                   \
+            rc = tangent_cfg(b, D4, c);                                                                            \
+            if (rc) return rc;                                                                                     \
+            rc = launch_tangent(k_tangent_general_ct<NN, DD>, st, b, c, x_vd, u, mask, values, K_e);               \
+        }                                                                                                          \
     } else
-    FEB_TANGENT_CASE(3, 2)
-    FEB_TANGENT_CASE(4, 2)
-    FEB_TANGENT_CASE(4, 3)
-    FEB_TANGENT_CASE(8, 3) {
-        if (iso) {   // the generic kernel stages the full D^4 tangent
-            rc = tangent_cfg(b, D4, c);
-            if (rc) return rc;
-        }
+    FEB_TANGENT_CASE(3, 2, 1)
+    FEB_TANGENT_CASE(4, 2, 1)
+    FEB_TANGENT_CASE(4, 3, 1)
+    FEB_TANGENT_CASE(8, 3, PASSES_HEX) {
+        rc = tangent_cfg(b, D4, c);     // the generic kernel stages the full D^4 tangent
+        if (rc) return rc;
         rc = (b.D == 2) ? launch_tangent(k_tangent_general_rt<2>, st, b, c, x_vd, u, mask, values, K_e)
                         : launch_tangent(k_tangent_general_rt<3>, st, b, c, x_vd, u, mask, values, K_e);
     }

@@ -15,7 +15,7 @@
 
 namespace feb {
 
-enum { S_GAMMA = 0, S_PAP = 1, S_RR = 2, S_ATOL2 = 3, S_GAMMA_NEW = 4, S_BB = 5 };
+enum { S_GAMMA = 0, S_PAP = 1, S_RR = 2, S_GAMMA_NEW = 3, S_ATOL2 = 4, S_BB = 5, S_TOL = 6, S_ATOL = 7 };
 enum { C_K = 0, C_DONE = 1, C_MAXITER = 2 };
 
 struct ReduceWs {
@@ -96,21 +96,27 @@ __global__ void k_spmv_csr(int64_t n_rows, const int64_t* __restrict__ indptr, c
 }
 
 __global__ void __launch_bounds__(256) k_dot(int64_t n, const double* __restrict__ a, const double* __restrict__ b,
-                                             double* out, ReduceWs ws) {
+                                             const double* __restrict__ w, double* out, ReduceWs ws,
+                                             const int32_t* counters) {
+    if (counters && counters[C_DONE]) return;
     double d[1] = {0.0};
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        d[0] += a[i] * b[i];
+        d[0] += w ? w[i] * (a[i] * b[i]) : a[i] * b[i];
     __shared__ double red[32];
     block_sum<1>(d, red);
     double total[1];
     if (grid_sum_last_block<1>(d, ws.part, ws.ticket, total)) out[0] = total[0];
 }
 
-// r = b - Ap(=A x0) ; z = M r ; p = z ; partial sums (r.z, r.r, b.b); last block initialises the loop state
-__global__ void __launch_bounds__(256) k_cg_init(int64_t n, const double* __restrict__ b, const double* __restrict__ Ax,
-                                                 const double* __restrict__ inv_diag, double* __restrict__ r,
-                                                 double* __restrict__ p, double* hist, double* scalars, int32_t* counters,
-                                                 ReduceWs ws, double tol, double atol, int maxiter) {
+// r = b - Ax ; z = M r ; p = z ; (weighted) partial sums r.z -> S_GAMMA_NEW, r.r -> S_RR, b.b -> S_BB.
+// With ownership weights `w` (multi-GPU) the three sums are LOCAL and the caller all-reduces
+// scalars[S_RR..S_GAMMA_NEW] and scalars[S_BB] before k_cg_init_finalize.
+__global__ void __launch_bounds__(256) k_cg_init_vectors(int64_t n, const double* __restrict__ b,
+                                                         const double* __restrict__ Ax,
+                                                         const double* __restrict__ inv_diag,
+                                                         const double* __restrict__ w, double* __restrict__ r,
+                                                         double* __restrict__ p, double* scalars, ReduceWs ws,
+                                                         double tol, double atol) {
     double d[3] = {0.0, 0.0, 0.0};
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double bi = b[i];
@@ -118,33 +124,39 @@ __global__ void __launch_bounds__(256) k_cg_init(int64_t n, const double* __rest
         const double zi = inv_diag ? ri * inv_diag[i] : ri;
         r[i] = ri;
         p[i] = zi;
-        d[0] += ri * zi;
-        d[1] += ri * ri;
-        d[2] += bi * bi;
+        const double wi = w ? w[i] : 1.0;
+        d[0] += wi * (ri * zi);
+        d[1] += wi * (ri * ri);
+        d[2] += wi * (bi * bi);
     }
     __shared__ double red[96];
     block_sum<3>(d, red);
     double t[3];
     if (grid_sum_last_block<3>(d, ws.part, ws.ticket, t)) {
-        const double atol2 = fmax(tol * tol * t[2], atol * atol);
-        scalars[S_GAMMA] = t[0];
+        scalars[S_GAMMA_NEW] = t[0];
         scalars[S_RR] = t[1];
         scalars[S_BB] = t[2];
-        scalars[S_ATOL2] = atol2;
-        scalars[S_GAMMA_NEW] = t[0];
         scalars[S_PAP] = 0.0;
-        if (maxiter > 0) hist[0] = sqrt(t[1]);
-        const double rs = inv_diag ? t[1] : t[0];
-        counters[C_K] = 0;
-        counters[C_MAXITER] = maxiter;
-        counters[C_DONE] = (rs > atol2 && 0 < maxiter) ? 0 : 1;
+        scalars[S_TOL] = tol;
+        scalars[S_ATOL] = atol;
     }
+}
+__global__ void k_cg_init_finalize(double* scalars, int32_t* counters, double* hist, int maxiter, int preconditioned) {
+    const double tol = scalars[S_TOL], atol = scalars[S_ATOL];
+    const double atol2 = fmax(tol * tol * scalars[S_BB], atol * atol);
+    scalars[S_ATOL2] = atol2;
+    scalars[S_GAMMA] = scalars[S_GAMMA_NEW];
+    if (maxiter > 0) hist[0] = sqrt(scalars[S_RR]);
+    const double rs = preconditioned ? scalars[S_RR] : scalars[S_GAMMA];
+    counters[C_K] = 0;
+    counters[C_MAXITER] = maxiter;
+    counters[C_DONE] = (rs > atol2 && 0 < maxiter) ? 0 : 1;
 }
 
 __global__ void __launch_bounds__(256) k_cg_update_xr(int64_t n, const double* __restrict__ p, const double* __restrict__ Ap,
-                                                      const double* __restrict__ inv_diag, double* __restrict__ x,
-                                                      double* __restrict__ r, double* hist, double* scalars,
-                                                      int32_t* counters, ReduceWs ws) {
+                                                      const double* __restrict__ inv_diag, const double* __restrict__ w,
+                                                      double* __restrict__ x, double* __restrict__ r, double* scalars,
+                                                      const int32_t* counters, ReduceWs ws) {
     if (counters[C_DONE]) return;
     const double alpha = scalars[S_GAMMA] / scalars[S_PAP];
     double d[2] = {0.0, 0.0};
@@ -153,8 +165,9 @@ __global__ void __launch_bounds__(256) k_cg_update_xr(int64_t n, const double* _
         const double ri = r[i] - alpha * Ap[i];
         r[i] = ri;
         const double zi = inv_diag ? ri * inv_diag[i] : ri;
-        d[0] += ri * zi;
-        d[1] += ri * ri;
+        const double wi = w ? w[i] : 1.0;
+        d[0] += wi * (ri * zi);
+        d[1] += wi * (ri * ri);
     }
     __shared__ double red[64];
     block_sum<2>(d, red);
@@ -162,14 +175,10 @@ __global__ void __launch_bounds__(256) k_cg_update_xr(int64_t n, const double* _
     if (grid_sum_last_block<2>(d, ws.part, ws.ticket, t)) {
         scalars[S_GAMMA_NEW] = t[0];
         scalars[S_RR] = t[1];
-        const int k = counters[C_K];
-        const int maxiter = counters[C_MAXITER];
-        if (k + 1 < maxiter) hist[k + 1] = sqrt(t[1]);     // the write at k+1 == maxiter is dropped (solve_cg.py:45)
     }
 }
 
-// p = z + beta p ; thread 0 of block 0 then advances the loop state (after everyone has read it:
-// the state update happens in a separate tiny kernel to avoid a grid-wide race)
+// p = z + beta p
 __global__ void __launch_bounds__(256) k_cg_update_p(int64_t n, const double* __restrict__ r,
                                                      const double* __restrict__ inv_diag, double* __restrict__ p,
                                                      const double* scalars, const int32_t* counters) {
@@ -180,11 +189,14 @@ __global__ void __launch_bounds__(256) k_cg_update_p(int64_t n, const double* __
         p[i] = zi + beta * p[i];
     }
 }
-__global__ void k_cg_advance(double* scalars, int32_t* counters, int preconditioned) {
+// loop state update (separate tiny kernel: every block of update_p has read gamma before it changes):
+// hist[k+1] = |r| (dropped when k+1 == maxiter, solve_cg.py:45), gamma <- gamma', k++, loop test.
+__global__ void k_cg_advance(double* scalars, int32_t* counters, double* hist, int preconditioned) {
     if (counters[C_DONE]) return;
     const double g = scalars[S_GAMMA_NEW];
     scalars[S_GAMMA] = g;
     const int k = counters[C_K] + 1;
+    if (k < counters[C_MAXITER]) hist[k] = sqrt(scalars[S_RR]);
     counters[C_K] = k;
     const double rs = preconditioned ? scalars[S_RR] : g;
     if (!(rs > scalars[S_ATOL2] && k < counters[C_MAXITER])) counters[C_DONE] = 1;
@@ -264,25 +276,75 @@ int feb200_spmv_csr(feb200_stream s, int64_t n_rows, const int64_t* indptr, cons
 int feb200_dot(feb200_stream s, int64_t n, const double* a, const double* b, double* out, void* ws, size_t ws_bytes) {
     FEB_REQUIRE(a && b && out && ws, FEB200_ERR_INVALID, "dot: null pointer");
     FEB_REQUIRE(ws_bytes >= REDUCE_WS_BYTES, FEB200_ERR_WORKSPACE, "dot: reduce workspace too small");
-    k_dot<<<reduce_grid(n, 256), 256, 0, as_stream(s)>>>(n, a, b, out, reduce_ws(ws));
+    k_dot<<<reduce_grid(n, 256), 256, 0, as_stream(s)>>>(n, a, b, nullptr, out, reduce_ws(ws), nullptr);
     FEB_CHECK_LAUNCH("dot");
+    return FEB200_OK;
+}
+
+}  // extern "C"
+
+static int cg_stage(cudaStream_t cs, const feb200_cg_state* st, int stage, double tol, double atol) {
+    const int64_t n = st->V * st->U;
+    ReduceWs r = reduce_ws(st->ws);
+    const int pre = st->inv_diag ? 1 : 0;
+    int rc = FEB200_OK;
+    switch (stage) {
+        case FEB200_CG_INIT_SPMV:
+            FEB_CUDA(cudaMemsetAsync(r.ticket, 0, REDUCE_CHANNELS * sizeof(unsigned int), cs));
+            FEB_CUDA(cudaMemsetAsync(st->hist, 0, (size_t)st->maxiter * sizeof(double), cs));
+            if (st->V > 0)
+                rc = spmv_dispatch(cs, st->V, st->U, st->nindptr, st->nindices, st->values, st->x, st->Ap, nullptr, r,
+                                   nullptr, nullptr);
+            break;
+        case FEB200_CG_INIT_VECTORS:
+            k_cg_init_vectors<<<reduce_grid(n, 256), 256, 0, cs>>>(n, st->b, st->Ap, st->inv_diag, st->weights, st->r,
+                                                                 st->p, st->scalars, r, tol, atol);
+            break;
+        case FEB200_CG_INIT_FINALIZE:
+            k_cg_init_finalize<<<1, 1, 0, cs>>>(st->scalars, st->counters, st->hist, st->maxiter, pre);
+            break;
+        case FEB200_CG_SPMV:     // Ap = A p (+ p.Ap when there are no ownership weights)
+            if (st->V > 0)
+                rc = spmv_dispatch(cs, st->V, st->U, st->nindptr, st->nindices, st->values, st->p, st->Ap, nullptr, r,
+                                   st->counters, st->weights ? nullptr : st->scalars);
+            break;
+        case FEB200_CG_PAP:      // weighted p.Ap -> scalars[1] (local; caller all-reduces)
+            k_dot<<<reduce_grid(n, 256), 256, 0, cs>>>(n, st->p, st->Ap, st->weights, st->scalars + S_PAP, r, st->counters);
+            break;
+        case FEB200_CG_UPDATE_XR:
+            k_cg_update_xr<<<reduce_grid(n, 256), 256, 0, cs>>>(n, st->p, st->Ap, st->inv_diag, st->weights, st->x, st->r,
+                                                              st->scalars, st->counters, r);
+            break;
+        case FEB200_CG_UPDATE_P:
+            k_cg_update_p<<<grid_for(n, 256), 256, 0, cs>>>(n, st->r, st->inv_diag, st->p, st->scalars, st->counters);
+            k_cg_advance<<<1, 1, 0, cs>>>(st->scalars, st->counters, st->hist, pre);
+            break;
+        default:
+            FEB_REQUIRE(false, FEB200_ERR_INVALID, "cg_stage: unknown stage %d", stage);
+    }
+    return rc;
+}
+
+extern "C" {
+
+int feb200_cg_stage(feb200_stream s, const feb200_cg_state* st, int32_t stage, double tol, double atol) {
+    int rc = check_cg(st);
+    if (rc) return rc;
+    rc = cg_stage(as_stream(s), st, stage, tol, atol);
+    if (rc) return rc;
+    FEB_CHECK_LAUNCH("cg_stage");
     return FEB200_OK;
 }
 
 int feb200_cg_init(feb200_stream s, const feb200_cg_state* st, double tol, double atol) {
     int rc = check_cg(st);
     if (rc) return rc;
+    FEB_REQUIRE(!st->weights, FEB200_ERR_INVALID, "cg_init: ownership weights need the staged API (all-reduce between stages)");
     cudaStream_t cs = as_stream(s);
-    const int64_t n = st->V * st->U;
-    ReduceWs r = reduce_ws(st->ws);
-    FEB_CUDA(cudaMemsetAsync(r.ticket, 0, REDUCE_CHANNELS * sizeof(unsigned int), cs));
-    FEB_CUDA(cudaMemsetAsync(st->hist, 0, (size_t)st->maxiter * sizeof(double), cs));
-    if (st->V > 0) {
-        rc = spmv_dispatch(cs, st->V, st->U, st->nindptr, st->nindices, st->values, st->x, st->Ap, nullptr, r, nullptr, nullptr);
+    for (int stage = FEB200_CG_INIT_SPMV; stage <= FEB200_CG_INIT_FINALIZE; ++stage) {
+        rc = cg_stage(cs, st, stage, tol, atol);
         if (rc) return rc;
     }
-    k_cg_init<<<reduce_grid(n, 256), 256, 0, cs>>>(n, st->b, st->Ap, st->inv_diag, st->r, st->p, st->hist, st->scalars,
-                                                 st->counters, r, tol, atol, st->maxiter);
     FEB_CHECK_LAUNCH("cg_init");
     return FEB200_OK;
 }
@@ -290,19 +352,13 @@ int feb200_cg_init(feb200_stream s, const feb200_cg_state* st, double tol, doubl
 int feb200_cg_iterate(feb200_stream s, const feb200_cg_state* st, int32_t n_iters) {
     int rc = check_cg(st);
     if (rc) return rc;
+    FEB_REQUIRE(!st->weights, FEB200_ERR_INVALID, "cg_iterate: ownership weights need the staged API");
     cudaStream_t cs = as_stream(s);
-    const int64_t n = st->V * st->U;
-    if (n == 0) return FEB200_OK;
-    ReduceWs r = reduce_ws(st->ws);
-    const int gv = reduce_grid(n, 256);
-    const int gp = grid_for(n, 256);
+    if (st->V * st->U == 0) return FEB200_OK;
     for (int it = 0; it < n_iters; ++it) {
-        rc = spmv_dispatch(cs, st->V, st->U, st->nindptr, st->nindices, st->values, st->p, st->Ap, nullptr, r, st->counters,
-                           st->scalars);
-        if (rc) return rc;
-        k_cg_update_xr<<<gv, 256, 0, cs>>>(n, st->p, st->Ap, st->inv_diag, st->x, st->r, st->hist, st->scalars, st->counters, r);
-        k_cg_update_p<<<gp, 256, 0, cs>>>(n, st->r, st->inv_diag, st->p, st->scalars, st->counters);
-        k_cg_advance<<<1, 1, 0, cs>>>(st->scalars, st->counters, st->inv_diag ? 1 : 0);
+        if ((rc = cg_stage(cs, st, FEB200_CG_SPMV, 0, 0))) return rc;
+        if ((rc = cg_stage(cs, st, FEB200_CG_UPDATE_XR, 0, 0))) return rc;
+        if ((rc = cg_stage(cs, st, FEB200_CG_UPDATE_P, 0, 0))) return rc;
     }
     FEB_CHECK_LAUNCH("cg_iterate");
     return FEB200_OK;

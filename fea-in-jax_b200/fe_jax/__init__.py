@@ -27,3 +27,4 @@ from .krylov import cg as cg_w_info
 from .solver import (PreconditionerType, LinearSolverType, SolverOptions, SolverResultInfo, init_solver_info,
                      Residual, Jacobian, JacobianDiagonl, linear_solve)
 from .newton import solve_nonlinear_step, solve_bvp
+from . import partition

@@ -18,6 +18,7 @@ FEB200_MAX_BATCHES = 16
 KIND_LINEAR, KIND_HYPER = 0, 1
 MAT_ISOTROPIC, MAT_ORTHOTROPIC, MAT_SVK, MAT_MOONEY_RIVLIN = 0, 1, 2, 3
 LAYOUT_M, LAYOUT_EM, LAYOUT_EQM = 0, 1, 2
+CG_INIT_SPMV, CG_INIT_VECTORS, CG_INIT_FINALIZE, CG_SPMV, CG_PAP, CG_UPDATE_XR, CG_UPDATE_P = range(7)
 
 
 class Feb200Error(RuntimeError):
@@ -38,7 +39,7 @@ class BatchMap(Structure):
 class CGState(Structure):
     _fields_ = [("V", c_int64), ("U", c_int32), ("maxiter", c_int32),
                 ("nindptr", c_void_p), ("nindices", c_void_p), ("values", c_void_p), ("inv_diag", c_void_p),
-                ("b", c_void_p), ("x", c_void_p), ("r", c_void_p), ("p", c_void_p), ("Ap", c_void_p),
+                ("weights", c_void_p), ("b", c_void_p), ("x", c_void_p), ("r", c_void_p), ("p", c_void_p), ("Ap", c_void_p),
                 ("hist", c_void_p), ("scalars", c_void_p), ("counters", c_void_p), ("ws", c_void_p),
                 ("ws_bytes", c_size_t)]
 
@@ -66,7 +67,7 @@ SIGNATURES = {
     "feb200_pattern_fill": (c_int32, [_P, POINTER(BatchMap), _I32, _I64, _P, _P, _P]),
     "feb200_slot_rank": (c_int32, [_P, _P, _I64, _I32, _P, _P, _P]),
     "feb200_pattern_expand": (c_int32, [_P, _I64, _I32, _P, _P, _P, _P, _P]),
-    "feb200_assemble_csr": (c_int32, [_P, POINTER(BatchMap), _I64, _I32, _P, _P, _P, _I32, _P, _I32]),
+    "feb200_assemble_csr": (c_int32, [_P, POINTER(BatchMap), _I64, _I32, _P, _P, _P, _I32, _P, _I32, _P, _P]),
     "feb200_dirichlet_lhs": (c_int32, [_P, _I64, _I32, _P, _P, _P, _P]),
     "feb200_dirichlet_lhs_coo": (c_int32, [_P, _I64, _P, _P, _P, _P, _P]),
     "feb200_csr_diagonal": (c_int32, [_P, _I64, _I32, _P, _P, _P, _P]),
@@ -80,6 +81,7 @@ SIGNATURES = {
     "feb200_dot": (c_int32, [_P, _I64, _P, _P, _P, _P, _SZ]),
     "feb200_cg_init": (c_int32, [_P, POINTER(CGState), _F64, _F64]),
     "feb200_cg_iterate": (c_int32, [_P, POINTER(CGState), _I32]),
+    "feb200_cg_stage": (c_int32, [_P, POINTER(CGState), _I32, _F64, _F64]),
     "feb200_axpby": (c_int32, [_P, _I64, _F64, _P, _F64, _P, _P]),
     "feb200_scatter_set": (c_int32, [_P, _I64, _P, _P, _F64, _P, _P]),
 }

@@ -319,7 +319,7 @@ def _as_u(ebc, u_f):
     return u
 
 
-def _residual(element_residual_func, ebc, assembly_map_b, u, mask, values):
+def _residual(element_residual_func, ebc, assembly_map_b, u, mask, values, fuse_dirichlet=True):
     res = resolve_residual(element_residual_func)
     F = u.shape[0]
     R = torch.empty(F, dtype=torch.float64, device=u.device)
@@ -332,7 +332,7 @@ def _residual(element_residual_func, ebc, assembly_map_b, u, mask, values):
         am = assembly_map_b[i]
         row = am.indptr.reshape(-1).view(torch.int64)
         col = am.indices.reshape(-1).view(torch.int64)
-        last = (i == ebc.B - 1) and mask is not None
+        last = (i == ebc.B - 1) and mask is not None and fuse_dirichlet
         _lib.call("feb200_scatter_sum", _lib.ptr(row), _lib.ptr(col), am.shape[1], ebc.U[i], _lib.ptr(R_e), _lib.ptr(R),
                   1 if i > 0 else 0, _lib.ptr(mask) if last else None, _lib.ptr(values) if last else None,
                   _lib.ptr(u) if last else None)
@@ -356,8 +356,9 @@ def calculate_residual_w_dirichlet(element_residual_func, ebc: ElementBatchColle
 
 
 # --------------------------------------------------------------------------------------------- Jacobian
-def _assemble_values(element_residual_func, ebc, assembly_map_b, u, mask=None, values=None, out=None):
-    """CSR values (reference order) of J(u) [or J(u_w) when a mask is given] on the node pattern."""
+def _assemble_values(element_residual_func, ebc, assembly_map_b, u, mask=None, values=None, out=None, eliminate=False):
+    """CSR values (reference order) of J(u) [or J(u_w) when a mask is given] on the node pattern.  With
+    `eliminate` the Dirichlet elimination (apply_dirichlet_bcs_lhs) is fused into the last batch's store."""
     res = resolve_residual(element_residual_func)
     plan = _plan(ebc, assembly_map_b)
     pat = plan.pattern
@@ -368,8 +369,10 @@ def _assemble_values(element_residual_func, ebc, assembly_map_b, u, mask=None, v
         _lib.call("feb200_element_tangent", b, _lib.ptr(ebc._vertices), _lib.ptr(u), _lib.ptr(mask), _lib.ptr(values),
                   _lib.ptr(K_e))
         bm = plan.maps[i]
+        elim = eliminate and mask is not None and i == ebc.B - 1
         _lib.call("feb200_assemble_csr", bm, pat.V, pat.U, _lib.ptr(K_e), _lib.ptr(plan.slot_rank[i]),
-                  _lib.ptr(pat.nindptr), pat.max_deg, _lib.ptr(vals), 1 if i > 0 else 0)
+                  _lib.ptr(pat.nindptr), pat.max_deg, _lib.ptr(vals), 1 if i > 0 else 0,
+                  _lib.ptr(pat.nindices) if elim else None, _lib.ptr(mask) if elim else None)
     return vals, pat
 
 

@@ -41,11 +41,12 @@ def solve_nonlinear_step(element_residual_func, ebc: ElementBatchCollection, ass
     def residual_func_w_dirichlet(u_f):
         return residual_isv_func_w_dirichlet(u_f)[0]
 
-    def jacobian_func_wo_dirichlet(u_f):
-        # assembled at u_w = (1-m) u + m g: this is the operator the reference's CG branch applies
-        # (JVP of R_w at x_0, sparse_linear_solve.py:251-258); identical to J(u_f) for linear problems
+    def jacobian_func_w_dirichlet(u_f):
+        # J_w = (I-M) J(u_w) (I-M) + M, assembled at u_w = (1-m) u + m g with the elimination fused into the
+        # assembly store: this is the operator the reference's CG branch applies (JVP of R_w at x_0,
+        # sparse_linear_solve.py:251-258); identical to apply_dirichlet_bcs_lhs(J(u_f)) for linear problems
         u = as_device(u_f, torch.float64)
-        vals, pat = _assemble_values(element_residual_func, ebc, assembly_map_b, u, mask_g, values_g)
+        vals, pat = _assemble_values(element_residual_func, ebc, assembly_map_b, u, mask_g, values_g, eliminate=True)
         if jacobian_nnz is not None and int(jacobian_nnz) != pat.nnz:
             raise _lib.Feb200Error(f"jacobian_nnz={jacobian_nnz} but the pattern has {pat.nnz} entries")
         return COO((vals,), shape=(u.shape[0], u.shape[0]), rows_sorted=True, pattern=pat)
@@ -70,7 +71,7 @@ def solve_nonlinear_step(element_residual_func, ebc: ElementBatchCollection, ass
             break
         delta_u, info = linear_solve(
             residual=Residual(function=residual_func_w_dirichlet, dirichlet_bcs_builtin=True),
-            jacobian=Jacobian(function=jacobian_func_wo_dirichlet, dirichlet_bcs_builtin=False),
+            jacobian=Jacobian(function=jacobian_func_w_dirichlet, dirichlet_bcs_builtin=True),
             jacobian_diagonal=JacobianDiagonl(function=jacobian_diag_func_wo_dirichlet, dirichlet_bcs_builtin=False),
             dirichlet_dofs=dirichlet_dofs, dirichlet_values=dirichlet_values, solver_options=solver_options,
             solver_info_0=info, check_consistency=False, x_0=u_f)

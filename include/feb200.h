@@ -143,10 +143,12 @@ int feb200_pattern_expand(feb200_stream s, int64_t V, int32_t U, const int64_t* 
 /* ------------------------------------------------------------------ deterministic CSR assembly
  * values (U*U*nnz_nodes) (+)= segmented sum of the element blocks, ascending element order per entry
  * (the order a stable (row,col) sort + sequential bincount gives, fea.py:651-658).
- * Replaces COO-concatenate + _sort_indices + coo_sum_duplicates. max_deg = max vertex degree. */
+ * Replaces COO-concatenate + _sort_indices + coo_sum_duplicates. max_deg = max vertex degree.
+ * If mask != NULL (with nindices) the Dirichlet elimination of feb200_dirichlet_lhs is applied to the
+ * finished sums while they are stored (pass it with the LAST batch only). */
 int feb200_assemble_csr(feb200_stream s, const feb200_batch_map* map, int64_t V, int32_t U, const double* K_e,
                         const uint16_t* slot_rank, const int64_t* nindptr, int32_t max_deg, double* values,
-                        int32_t accumulate);
+                        int32_t accumulate, const int32_t* nindices, const double* mask);
 /* apply_dirichlet_bcs_lhs on the node-pattern CSR (sparse_matrix.py:157-184). mask: (U*V) 0/1 doubles. */
 int feb200_dirichlet_lhs(feb200_stream s, int64_t V, int32_t U, const int64_t* nindptr, const int32_t* nindices,
                          const double* mask, double* values);
@@ -179,7 +181,7 @@ int feb200_spmv_csr(feb200_stream s, int64_t n_rows, const int64_t* indptr, cons
 /* out[0] = a.b */
 int feb200_dot(feb200_stream s, int64_t n, const double* a, const double* b, double* out, void* ws, size_t ws_bytes);
 
-/* Device-resident CG state: scalars (double[8]) = {gamma, pAp, rr, atol2, gamma_new, bb, -, -},
+/* Device-resident CG state: scalars (double[8]) = {gamma, pAp, rr, gamma_new, atol2, bb, tol, atol},
  * counters (int32[4]) = {k, done, maxiter, -}.  cg_init computes r0 = b - A x0, z0 = M r0, p0 = z0,
  * gamma0, atol2 = max(tol^2 b.b, atol^2), hist[0] = |r0| and the first loop test; cg_iterate enqueues
  * `n_iters` iterations whose kernels exit at once when `done` is set, so the caller may enqueue maxiter
@@ -193,6 +195,7 @@ typedef struct {
     const int32_t* nindices;
     const double* values;
     const double* inv_diag;   /* may be NULL */
+    const double* weights;    /* may be NULL; multi-GPU ownership weights (1 = DoF owned by this rank, else 0) */
     const double* b;
     double* x;                /* in: x0, out: solution */
     double* r;
@@ -206,6 +209,13 @@ typedef struct {
 } feb200_cg_state;
 int feb200_cg_init(feb200_stream s, const feb200_cg_state* st, double tol, double atol);
 int feb200_cg_iterate(feb200_stream s, const feb200_cg_state* st, int32_t n_iters);
+/* The same loop cut into stages, so that an element-partitioned multi-GPU driver can put the interface
+ * halo-sum (after the SpMV stages) and the scalar all-reduces (after INIT_VECTORS: scalars[2,3,5]; after PAP:
+ * scalars[1]; after UPDATE_XR: scalars[2,3]) between them.  With `weights` the dot products count every DoF
+ * once (owned DoFs only). */
+typedef enum { FEB200_CG_INIT_SPMV = 0, FEB200_CG_INIT_VECTORS = 1, FEB200_CG_INIT_FINALIZE = 2, FEB200_CG_SPMV = 3,
+               FEB200_CG_PAP = 4, FEB200_CG_UPDATE_XR = 5, FEB200_CG_UPDATE_P = 6 } feb200_cg_stage_id;
+int feb200_cg_stage(feb200_stream s, const feb200_cg_state* st, int32_t stage, double tol, double atol);
 
 /* fused vector helpers used by linear_solve / Newton (sparse_linear_solve.py:287-292, 527; fea.py:1103) */
 int feb200_axpby(feb200_stream s, int64_t n, double a, const double* x, double b, const double* y, double* out);
