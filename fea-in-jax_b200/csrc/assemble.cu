@@ -80,7 +80,7 @@ __global__ void k_assemble_csr(const unsigned long long* __restrict__ row_ind, c
 // of up to PD incident slots are loaded first (PD*U independent 8-byte loads in flight per lane), then
 // added in slot order.
 template <int U, int PD>
-__global__ void __launch_bounds__(256) k_assemble_csr_pre(const unsigned long long* __restrict__ row_ind,
+__global__ void __launch_bounds__(256, 4) k_assemble_csr_pre(const unsigned long long* __restrict__ row_ind,
                                                           const unsigned long long* __restrict__ col_ind, int64_t V, int N,
                                                           const double* __restrict__ K_e,
                                                           const uint16_t* __restrict__ slot_rank,
@@ -246,7 +246,7 @@ int feb200_assemble_csr(feb200_stream s, const feb200_batch_map* map, int64_t V,
 #define FEB_ASM(UU)                                                                                                    \
     {                                                                                                                  \
         if (fast) {                                                                                                    \
-            auto kern = k_assemble_csr_pre<UU, 8>;                                                                     \
+            auto kern = k_assemble_csr_pre<UU, 4>;                                                                     \
             if (smem > 48 * 1024) FEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             kern<<<(int)g, wpb * 32, smem, st>>>(ri, ci, V, map->N, K_e, slot_rank, nindptr, max_deg, values, accumulate, \
                                                  nindices, mask);                                                      \

@@ -64,6 +64,14 @@ constexpr int REDUCE_CHANNELS = 4;     // independent ticket counters
 constexpr size_t REDUCE_WS_BYTES = (size_t)MAX_PARTIALS * 4 * sizeof(double) + REDUCE_CHANNELS * sizeof(unsigned int) + 64;
 
 #if defined(__CUDACC__)
+// material parameters of element e (layouts of fea.py:77-80): pointer to quadrature point 0 and the stride
+// between quadrature points (0 when the parameters are constant over the element)
+__device__ __forceinline__ const double* mp_of(const feb200_batch& b, int64_t e, int& q_stride) {
+    if (b.layout == FEB200_LAYOUT_EQM) { q_stride = b.M; return b.mp + (e * b.Q) * (int64_t)b.M; }
+    q_stride = 0;
+    return (b.layout == FEB200_LAYOUT_EM) ? b.mp + e * (int64_t)b.M : b.mp;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -12,12 +12,6 @@
 
 namespace feb {
 
-__device__ __forceinline__ const double* mp_of(const feb200_batch& b, int64_t e, int& q_stride) {
-    if (b.layout == LAYOUT_EQM) { q_stride = b.M; return b.mp + (e * b.Q) * (int64_t)b.M; }
-    q_stride = 0;
-    return (b.layout == LAYOUT_EM) ? b.mp + e * (int64_t)b.M : b.mp;
-}
-
 __device__ __forceinline__ double load_u(const double* __restrict__ u, const double* __restrict__ mask,
                                          const double* __restrict__ values, int64_t f) {
     const double v = u[f];
@@ -193,6 +187,7 @@ __global__ void __launch_bounds__(128) k_tangent_iso(feb200_batch b, int epb, in
     constexpr int NU = N * D, D2 = D * D;
     constexpr int NB = N / PASSES;                  // blocks per pass
     constexpr int PIECE = NB * D2;                  // doubles per thread and pass
+    constexpr int PSTRIDE = PIECE | 1;              // odd shared-memory stride: conflict-free staging writes
     static_assert(N % PASSES == 0, "PASSES must divide N");
     extern __shared__ double smem[];
     double* s_dphi = smem;
@@ -282,7 +277,7 @@ __global__ void __launch_bounds__(128) k_tangent_iso(feb200_batch b, int epb, in
         for (int pass = 0; pass < PASSES; ++pass) {
             __syncthreads();                                                     // geometry / previous pass consumed
             if (active) {
-                double* dst = s_el + (size_t)threadIdx.x * PIECE;
+                double* dst = s_el + (size_t)threadIdx.x * PSTRIDE;
 #pragma unroll
                 for (int bn = 0; bn < NB; ++bn)
 #pragma unroll
@@ -292,7 +287,7 @@ __global__ void __launch_bounds__(128) k_tangent_iso(feb200_batch b, int epb, in
             for (int64_t i = threadIdx.x; i < n_slots * PIECE; i += blockDim.x) {
                 const int64_t t = i / PIECE;
                 const int c = (int)(i - t * PIECE);
-                K_e[(slot0 + t) * (int64_t)(N * D2) + pass * PIECE + c] = s_el[t * PIECE + c];
+                K_e[(slot0 + t) * (int64_t)(N * D2) + pass * PIECE + c] = s_el[t * PSTRIDE + c];
             }
         }
         (void)n_slots_blk;
@@ -446,6 +441,7 @@ static int tangent_cfg(const feb200_batch& b, int aux, TangentCfg& c, int max_th
     const int NU = b.N * b.D;
     c.per_el = 2 * NU + b.Q * NU + b.Q + b.Q * aux;
     if (c.per_el < stage_doubles_per_thread * b.N) c.per_el = stage_doubles_per_thread * b.N;   // store staging aliases it
+    while (c.per_el % 16 != 4) ++c.per_el;   // elements of one warp hit distinct shared-memory banks on broadcast reads
     const size_t table = (size_t)b.Q * NU * sizeof(double);
     const size_t budget = 96 * 1024;
     int epb = max_threads / b.N;
@@ -513,7 +509,7 @@ int feb200_element_tangent(feb200_stream s, const feb200_batch* bp, const double
 #define FEB_TANGENT_CASE(NN, DD, PP)                                                                               \
     if (b.N == NN && b.D == DD) {                                                                                  \
         if (iso) {                                                                                                 \
-            rc = tangent_cfg(b, 2, c, 128, (NN / PP) * DD * DD);                                                   \
+            rc = tangent_cfg(b, 2, c, 128, ((NN / PP) * DD * DD) | 1);                                                   \
             if (rc) return rc;                                                                                     \
             rc = cm ? launch_tangent(k_tangent_iso<NN, DD, true, PP>, st, b, c, x_vd, u, mask, values, K_e)        \
                     : launch_tangent(k_tangent_iso<NN, DD, false, PP>, st, b, c, x_vd, u, mask, values, K_e);      \

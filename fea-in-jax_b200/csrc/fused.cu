@@ -1,0 +1,269 @@
+// Fused hex8 assembly: element tangents are computed and summed into the CSR row panels inside one
+// kernel, so K_e never goes to HBM (the two-pass path of element.cu + assemble.cu moves ~5x the
+// algorithmic bytes).  Replaces, for linear isotropic hex8 batches,
+//   vmap(jacfwd(residual_kernel))            /root/reference/src/fe_jax/fea.py:519-572
+//   COO concat + sort + coo_sum_duplicates   fea.py:613-660, src/fe_jax/sparse_matrix.py:44-110
+//   apply_dirichlet_bcs_lhs                  sparse_matrix.py:157-184 (optional, fused into the store)
+//
+// Work decomposition ("tile plan", built once per mesh by fe_jax/fused_plan.py, any connectivity):
+//   tile  = up to TN vertices that are close in space (Morton cell) -> one CTA, 8 threads per vertex
+//   P1    geometry of every element touching the tile, once per tile: g[le][n][q][3], detJ*W   -> smem
+//   P2    one thread per (vertex a, incident slot k): the block row K_e[a, 0..8) of that element from the
+//         staged gradients: S_ab = sum_q w g_a (x) g_b (72 FMA), K_ab = lam S + mu S^T + mu tr(S) I
+//   P3    block rows to shared memory (aliases the gradients)
+//   P4    one lane per CSR block (a, r): adds the <= 8 contributions in ascending slot order -- the order
+//         a stable (row, col) sort + bincount gives -- applies the Dirichlet elimination and stores the
+//         panel entries (coalesced).  No atomics; bit-reproducible.
+#include "common.cuh"
+#include "element_math.cuh"
+
+namespace feb {
+
+constexpr int FUSED_N = 8, FUSED_Q = 8, FUSED_D = 3;
+constexpr int FUSED_MAXVAL = 8;          // threads per vertex = max incident slots handled
+constexpr int G_STRIDE = 26;             // doubles per (element, node) gradient record (24 used): 16-byte aligned,
+                                         // consecutive records start 20 banks apart
+constexpr int BLK_STRIDE = 73;           // doubles per (vertex, slot) block row in the staging area (72 used, odd)
+
+struct FusedSmem {
+    int tn_cap, te_cap;
+    size_t off_stage, off_xs, off_dphi, off_lm, off_ints, total;
+};
+static inline FusedSmem fused_layout(int tn_cap, int te_cap) {
+    FusedSmem L;
+    L.tn_cap = tn_cap;
+    L.te_cap = te_cap;
+    size_t g_doubles = (size_t)te_cap * FUSED_N * G_STRIDE + (size_t)te_cap * FUSED_Q;      // G + wdet
+    size_t st_doubles = (size_t)tn_cap * FUSED_MAXVAL * BLK_STRIDE;
+    size_t a = g_doubles > st_doubles ? g_doubles : st_doubles;
+    a = (a + 1) & ~(size_t)1;
+    L.off_stage = 0;
+    L.off_xs = a * 8;
+    L.off_dphi = L.off_xs + (size_t)te_cap * 24 * 8;
+    L.off_lm = L.off_dphi + (size_t)FUSED_Q * 24 * 8;
+    L.off_ints = L.off_lm + (size_t)te_cap * 2 * 8;
+    // ints: conn_s[te*8] i32, p0[tn] i64 (first, 8-aligned), node[tn] i32, deg[tn] i32, val[tn] i32, rk[tn*8*8] u16
+    L.total = L.off_ints + (size_t)tn_cap * 8 + (size_t)te_cap * 8 * 4 + (size_t)tn_cap * 4 * 3 +
+              (size_t)tn_cap * 64 * 2 + 64;
+    return L;
+}
+
+template <bool ELIM>
+__global__ void __launch_bounds__(256, 1)
+k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const double* __restrict__ x_vd,
+                 const unsigned long long* __restrict__ row_ind, const uint16_t* __restrict__ slot_rank,
+                 const int64_t* __restrict__ nindptr, const int32_t* __restrict__ nindices,
+                 const double* __restrict__ mask, double* __restrict__ values) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* G = reinterpret_cast<double*>(smem_raw + L.off_stage);          // [le][n][G_STRIDE] : g[q][3]
+    double* wdet = G + (size_t)L.te_cap * FUSED_N * G_STRIDE;               // [le][q]
+    double* stage = reinterpret_cast<double*>(smem_raw + L.off_stage);      // [a][k][BLK_STRIDE]  (aliases G)
+    double* xs = reinterpret_cast<double*>(smem_raw + L.off_xs);            // [le][n][3]
+    double* s_dphi = reinterpret_cast<double*>(smem_raw + L.off_dphi);      // [q][n][3]
+    double* lm = reinterpret_cast<double*>(smem_raw + L.off_lm);            // [le][2] lambda, mu
+    int64_t* p0_s = reinterpret_cast<int64_t*>(smem_raw + L.off_ints);      // [a]
+    int32_t* conn_s = reinterpret_cast<int32_t*>(p0_s + L.tn_cap);          // [le][8]
+    int32_t* node_s = conn_s + (size_t)L.te_cap * 8;                        // [a]
+    int32_t* deg_s = node_s + L.tn_cap;
+    int32_t* val_s = deg_s + L.tn_cap;
+    uint16_t* rk_s = reinterpret_cast<uint16_t*>(val_s + L.tn_cap);         // [a][k][8]
+
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    for (int i = tid; i < FUSED_Q * 24; i += nthr) s_dphi[i] = b.dphi[i];
+
+    for (int tile = blockIdx.x; tile < plan.n_tiles; tile += gridDim.x) {
+        const int n0 = plan.tile_node_ptr[tile], TN = plan.tile_node_ptr[tile + 1] - n0;
+        const int e0 = plan.tile_elem_ptr[tile], TE = plan.tile_elem_ptr[tile + 1] - e0;
+        const int i0 = plan.tile_item_ptr[tile], NI = plan.tile_item_ptr[tile + 1] - i0;
+        __syncthreads();                                     // previous tile fully consumed
+        // ---- P0: tile metadata, connectivity, coordinates
+        for (int a = tid; a < TN; a += nthr) {
+            const int node = plan.tile_nodes[n0 + a];
+            node_s[a] = node;
+            const int64_t p0 = nindptr[node];
+            p0_s[a] = p0;
+            deg_s[a] = (int)(nindptr[node + 1] - p0);
+            val_s[a] = (int)(row_ind[node + 1] - row_ind[node]);
+        }
+        for (int i = tid; i < TE * 8; i += nthr) {
+            const int le = i >> 3, n = i & 7;
+            const int64_t e = plan.tile_elems[e0 + le];
+            const int32_t v = b.conn[e * 8 + n];
+            conn_s[i] = v;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) xs[i * 3 + d] = x_vd[(int64_t)v * 3 + d];
+            if (n == 0) {
+                int qs;
+                const double* mp = mp_of(b, e, qs);
+                double lam, mu;
+                isotropic_lame<3>(mp, lam, mu);
+                lm[le * 2] = lam;
+                lm[le * 2 + 1] = mu;
+            }
+        }
+        __syncthreads();
+        // ---- P1: geometry, one thread per (element, quadrature point)
+        for (int i = tid; i < TE * 8; i += nthr) {
+            const int le = i >> 3, q = i & 7;
+            double g[24];
+            const double dt = shape_gradients<8, 3>(xs + le * 24, s_dphi + q * 24, g);
+            wdet[i] = dt * b.W[q];
+#pragma unroll
+            for (int n = 0; n < 8; ++n)
+#pragma unroll
+                for (int d = 0; d < 3; ++d) G[(size_t)(le * 8 + n) * G_STRIDE + q * 3 + d] = g[n * 3 + d];
+        }
+        __syncthreads();
+        // ---- P2: block rows, one thread per (vertex, incident slot); items are sorted by element so that the
+        //          lanes of a warp read few distinct gradient records (broadcast)
+        double blk[8][9];
+        int a_loc = 0, kk = 0;
+        const bool has_item = tid < NI;
+        if (has_item) {
+            const uint32_t it = plan.tile_items[i0 + tid];
+            const int le = it & 0xfff, na = (it >> 12) & 0xf;
+            a_loc = (it >> 16) & 0xff;
+            kk = (it >> 24) & 0xff;
+            const int64_t slot = (int64_t)plan.tile_elems[e0 + le] * 8 + na;
+            // ranks of the 8 neighbours of this slot: one 16-byte load
+            const uint4 rk8 = *reinterpret_cast<const uint4*>(slot_rank + slot * 8);
+            *reinterpret_cast<uint4*>(rk_s + (size_t)(a_loc * FUSED_MAXVAL + kk) * 8) = rk8;
+            double wga[8][3];
+            {
+                const double2* rec = reinterpret_cast<const double2*>(G + (size_t)(le * 8 + na) * G_STRIDE);
+                double tmp[24];
+#pragma unroll
+                for (int j = 0; j < 12; ++j) { const double2 v = rec[j]; tmp[2 * j] = v.x; tmp[2 * j + 1] = v.y; }
+                const double* w = wdet + le * 8;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) wga[q][d] = w[q] * tmp[q * 3 + d];
+            }
+            const double lam = lm[le * 2], mu = lm[le * 2 + 1];
+#pragma unroll
+            for (int bn = 0; bn < 8; ++bn) {
+                const double2* rec = reinterpret_cast<const double2*>(G + (size_t)(le * 8 + bn) * G_STRIDE);
+                double S[9];
+#pragma unroll
+                for (int c = 0; c < 9; ++c) S[c] = 0.0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {                  // 3 double2 = 6 doubles = 2 quadrature points
+                    const double2 v0 = rec[3 * j], v1 = rec[3 * j + 1], v2 = rec[3 * j + 2];
+                    const double gb0[3] = {v0.x, v0.y, v1.x}, gb1[3] = {v1.y, v2.x, v2.y};
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+#pragma unroll
+                        for (int l = 0; l < 3; ++l) {
+                            S[i * 3 + l] += wga[2 * j][i] * gb0[l];
+                            S[i * 3 + l] += wga[2 * j + 1][i] * gb1[l];
+                        }
+                }
+                const double tr = mu * (S[0] + S[4] + S[8]);
+#pragma unroll
+                for (int d = 0; d < 3; ++d)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        blk[bn][d * 3 + k] = lam * S[d * 3 + k] + mu * S[k * 3 + d] + (d == k ? tr : 0.0);
+            }
+        }
+        __syncthreads();                                     // all gradient reads done: staging may overwrite them
+        // ---- P3: block rows to shared memory
+        if (has_item) {
+            double* dst = stage + (size_t)(a_loc * FUSED_MAXVAL + kk) * BLK_STRIDE;
+#pragma unroll
+            for (int bn = 0; bn < 8; ++bn)
+#pragma unroll
+                for (int c = 0; c < 9; ++c) dst[bn * 9 + c] = blk[bn][c];
+        }
+        __syncthreads();
+        // ---- P4: one warp per vertex, one lane per neighbour block; contributions added in ascending slot order
+        const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+        for (int a = warp; a < TN; a += nwarp) {
+            const int deg = deg_s[a], val = val_s[a];
+            const int64_t node = node_s[a], p0 = p0_s[a];
+            const int row_len = 3 * deg;
+            for (int r = lane; r < deg; r += 32) {
+                double acc[9];
+#pragma unroll
+                for (int c = 0; c < 9; ++c) acc[c] = 0.0;
+                for (int k = 0; k < val; ++k) {
+                    const uint4 rk8 = *reinterpret_cast<const uint4*>(rk_s + (size_t)(a * FUSED_MAXVAL + k) * 8);
+                    const unsigned int w4[4] = {rk8.x, rk8.y, rk8.z, rk8.w};
+                    int bsel = -1;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if ((int)(w4[j] & 0xffffu) == r) bsel = 2 * j;
+                        if ((int)(w4[j] >> 16) == r) bsel = 2 * j + 1;
+                    }
+                    if (bsel >= 0) {
+                        const double* src = stage + (size_t)(a * FUSED_MAXVAL + k) * BLK_STRIDE + bsel * 9;
+#pragma unroll
+                        for (int c = 0; c < 9; ++c) acc[c] += src[c];
+                    }
+                }
+                double* dst = values + 9 * p0 + 3 * r;
+                if (ELIM) {
+                    const int64_t colv = nindices[p0 + r];
+                    bool cm[3], rm[3];
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) { cm[j] = mask[colv * 3 + j] != 0.0; rm[j] = mask[node * 3 + j] != 0.0; }
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+#pragma unroll
+                        for (int j = 0; j < 3; ++j)
+                            if (rm[i] || cm[j]) acc[i * 3 + j] = (rm[i] && colv == node && i == j) ? 1.0 : 0.0;
+                }
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) __stcs(dst + (int64_t)i * row_len + j, acc[i * 3 + j]);
+            }
+        }
+    }
+}
+
+}  // namespace feb
+
+using namespace feb;
+
+extern "C" {
+
+size_t feb200_fused_smem_bytes(int32_t tn_cap, int32_t te_cap) { return fused_layout(tn_cap, te_cap).total; }
+
+int feb200_assemble_fused_hex8(feb200_stream s, const feb200_batch* bp, const feb200_fused_plan* plan, const double* x_vd,
+                               const uint64_t* row_ind, const uint16_t* slot_rank, const int64_t* nindptr,
+                               const int32_t* nindices, const double* mask, double* values) {
+    FEB_REQUIRE(bp && plan && x_vd && row_ind && slot_rank && nindptr && nindices && values, FEB200_ERR_INVALID,
+                "assemble_fused_hex8: null pointer");
+    const feb200_batch& b = *bp;
+    FEB_REQUIRE(b.N == 8 && b.Q == 8 && b.D == 3, FEB200_ERR_UNSUPPORTED, "assemble_fused_hex8: needs hex8 with 8 quadrature points");
+    FEB_REQUIRE(b.kind == FEB200_KIND_LINEAR && b.material == FEB200_MAT_ISOTROPIC && b.layout != FEB200_LAYOUT_EQM,
+                FEB200_ERR_UNSUPPORTED, "assemble_fused_hex8: needs linear isotropic material, constant per element");
+    FEB_REQUIRE(b.conn && b.dphi && b.W && b.mp && b.M >= 2, FEB200_ERR_INVALID, "assemble_fused_hex8: bad batch");
+    FEB_REQUIRE(plan->tile_node_ptr && plan->tile_nodes && plan->tile_elem_ptr && plan->tile_elems && plan->tile_item_ptr &&
+                    plan->tile_items && plan->n_tiles >= 0,
+                FEB200_ERR_INVALID, "assemble_fused_hex8: bad plan");
+    FEB_REQUIRE(plan->tn_cap > 0 && plan->tn_cap % 4 == 0 && plan->tn_cap * FUSED_MAXVAL <= 256 && plan->te_cap > 0 &&
+                    plan->te_cap < 4096,
+                FEB200_ERR_INVALID, "assemble_fused_hex8: plan capacities tn=%d te=%d out of range", plan->tn_cap, plan->te_cap);
+    if (plan->n_tiles == 0) return FEB200_OK;
+    const FusedSmem L = fused_layout(plan->tn_cap, plan->te_cap);
+    FEB_REQUIRE(L.total <= 227 * 1024, FEB200_ERR_CAPACITY, "assemble_fused_hex8: tile needs %zu bytes of shared memory", L.total);
+    cudaStream_t st = as_stream(s);
+    const unsigned long long* ri = reinterpret_cast<const unsigned long long*>(row_ind);
+    int grid = plan->n_tiles < sm_count() ? plan->n_tiles : sm_count();
+    if (mask) {
+        auto kern = k_fused_hex8_iso<true>;
+        FEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+        kern<<<grid, 256, L.total, st>>>(b, *plan, L, x_vd, ri, slot_rank, nindptr, nindices, mask, values);
+    } else {
+        auto kern = k_fused_hex8_iso<false>;
+        FEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+        kern<<<grid, 256, L.total, st>>>(b, *plan, L, x_vd, ri, slot_rank, nindptr, nindices, mask, values);
+    }
+    FEB_CHECK_LAUNCH("assemble_fused_hex8");
+    return FEB200_OK;
+}
+
+}  // extern "C"

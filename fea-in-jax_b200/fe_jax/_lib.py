@@ -36,6 +36,12 @@ class BatchMap(Structure):
                 ("conn", c_void_p), ("row_ind", c_void_p), ("col_ind", c_void_p)]
 
 
+class FusedPlan(Structure):
+    _fields_ = [("n_tiles", c_int32), ("tn_cap", c_int32), ("te_cap", c_int32), ("reserved", c_int32),
+                ("tile_node_ptr", c_void_p), ("tile_nodes", c_void_p), ("tile_elem_ptr", c_void_p),
+                ("tile_elems", c_void_p), ("tile_item_ptr", c_void_p), ("tile_items", c_void_p)]
+
+
 class CGState(Structure):
     _fields_ = [("V", c_int64), ("U", c_int32), ("maxiter", c_int32),
                 ("nindptr", c_void_p), ("nindices", c_void_p), ("values", c_void_p), ("inv_diag", c_void_p),
@@ -68,6 +74,8 @@ SIGNATURES = {
     "feb200_slot_rank": (c_int32, [_P, _P, _I64, _I32, _P, _P, _P]),
     "feb200_pattern_expand": (c_int32, [_P, _I64, _I32, _P, _P, _P, _P, _P]),
     "feb200_assemble_csr": (c_int32, [_P, POINTER(BatchMap), _I64, _I32, _P, _P, _P, _I32, _P, _I32, _P, _P]),
+    "feb200_fused_smem_bytes": (_SZ, [_I32, _I32]),
+    "feb200_assemble_fused_hex8": (c_int32, [_P, POINTER(Batch), POINTER(FusedPlan), _P, _P, _P, _P, _P, _P, _P]),
     "feb200_dirichlet_lhs": (c_int32, [_P, _I64, _I32, _P, _P, _P, _P]),
     "feb200_dirichlet_lhs_coo": (c_int32, [_P, _I64, _P, _P, _P, _P, _P]),
     "feb200_csr_diagonal": (c_int32, [_P, _I64, _I32, _P, _P, _P, _P]),

@@ -282,6 +282,19 @@ class _Plan:
             _lib.call("feb200_slot_rank", _lib.ptr(ebc._conn32[i]), ebc.E[i], ebc.N[i], _lib.ptr(nindptr),
                       _lib.ptr(nindices), _lib.ptr(sr))
             self.slot_rank.append(sr)
+        self._fused = {}
+
+    def fused_plan(self, ebc, i):
+        """Tile plan of the fused hex8 kernel for batch i (None when the batch / mesh is not eligible)."""
+        if i not in self._fused:
+            plan = None
+            if (os.environ.get("FEB200_FUSED", "1") != "0" and ebc.B == 1 and ebc.N[i] == 8 and ebc.Q[i] == 8
+                    and ebc.D == 3):
+                from .fused_plan import build_fused_plan
+                row, col = self._keep[i]
+                plan = build_fused_plan(ebc._vertices, ebc._conn32[i], row, col)
+            self._fused[i] = plan
+        return self._fused[i]
 
 
 def _plan(ebc, assembly_map_b) -> _Plan:
@@ -365,6 +378,15 @@ def _assemble_values(element_residual_func, ebc, assembly_map_b, u, mask=None, v
     vals = out if out is not None else torch.empty(pat.nnz, dtype=torch.float64, device=u.device)
     for i in range(ebc.B):
         b = ebc._batch_struct(i, res.kind)
+        # fused path: linear isotropic hex8, material constant per element, single batch (tangent independent of u)
+        if (b.kind == _lib.KIND_LINEAR and b.material == _lib.MAT_ISOTROPIC and b.layout != _lib.LAYOUT_EQM
+                and plan.fused_plan(ebc, i) is not None):
+            fp = plan.fused_plan(ebc, i)
+            elim = eliminate and mask is not None
+            _lib.call("feb200_assemble_fused_hex8", b, fp.struct, _lib.ptr(ebc._vertices), _lib.ptr(plan._keep[i][0]),
+                      _lib.ptr(plan.slot_rank[i]), _lib.ptr(pat.nindptr), _lib.ptr(pat.nindices),
+                      _lib.ptr(mask) if elim else None, _lib.ptr(vals))
+            continue
         K_e = ebc._buffer("K_e", ebc.E[i] * ebc.N[i] * ebc.N[i] * ebc.U[i] * ebc.U[i])
         _lib.call("feb200_element_tangent", b, _lib.ptr(ebc._vertices), _lib.ptr(u), _lib.ptr(mask), _lib.ptr(values),
                   _lib.ptr(K_e))

@@ -461,3 +461,48 @@ def test_full_size_hex8_properties(fj, n):
     assert float(R.reshape(-1, 3).sum(0).abs().max()) <= 1e-9 * float(R.abs().sum())   # forces balance
     J2 = fj.calculate_jacobian_wo_dirichlet(fj.linear_elasticity_residual, ebc, maps, u, nnz)
     assert torch.equal(J.data, J2.data)
+
+
+# ------------------------------------------------------------------------------------------ fused assembly kernel
+@pytest.mark.parametrize("n,layout,shuffle", [(5, "M", False), (7, "EM", False), (6, "M", True), (9, "EM", True)])
+def test_fused_hex8_assembly_matches_two_pass_and_oracle(fj, n, layout, shuffle):
+    """feb200_assemble_fused_hex8 (tile plan, K_e never in HBM) against the two-pass path and the oracle,
+    with and without the fused Dirichlet elimination; non-cubic grid and shuffled element order included."""
+    from fe_jax.assembly import _assemble_values, _plan
+    Vx, cells = orc.uniform_hex_grid(n, n + 1, n - 1)
+    rng = np.random.default_rng(n)
+    Vx = Vx + 0.15 / n * rng.uniform(-1, 1, size=Vx.shape)
+    if shuffle:
+        cells = cells[rng.permutation(cells.shape[0])]
+    mp = material_params("elastic_isotropic", 3, {"M": (), "EM": (cells.shape[0],)}[layout], seed=2)
+    ebc, maps, token, prob, _ = build_pair(fj, Vx, [dict(cell="hexahedron", degree=1, qdeg=2, cells=cells,
+                                                        model="elastic_isotropic", mp=mp)])
+    u = 1e-3 * rng.normal(size=Vx.size)
+    ud = torch.tensor(u, device="cuda")
+    assert _plan(ebc, maps).fused_plan(ebc, 0) is not None
+    stats = _plan(ebc, maps).fused_plan(ebc, 0).stats
+    assert stats["element_visits_per_element"] < 6.0
+    v_fused, pat = _assemble_values(token, ebc, maps, ud)
+    os.environ["FEB200_FUSED"] = "0"
+    try:
+        ebc2, maps2, _, _, _ = build_pair(fj, Vx, [dict(cell="hexahedron", degree=1, qdeg=2, cells=cells,
+                                                       model="elastic_isotropic", mp=mp)])
+        assert _plan(ebc2, maps2).fused_plan(ebc2, 0) is None
+        v_two, _ = _assemble_values(token, ebc2, maps2, ud)
+    finally:
+        os.environ["FEB200_FUSED"] = "1"
+    d_o, r_o, c_o = prob.jacobian_wo_dirichlet(u)
+    assert rel_err(v_fused, d_o) <= ASM_RTOL and rel_err(v_two, d_o) <= ASM_RTOL
+    assert rel_err(v_fused, v_two.cpu().numpy()) <= 1e-14
+    # fused elimination
+    bc_nodes = np.nonzero(Vx[:, 0] < 0.1)[0]
+    dofs = np.concatenate([3 * bc_nodes, 3 * bc_nodes[::2] + 2])
+    mask = torch.zeros(prob.F, dtype=torch.float64, device="cuda")
+    mask[torch.tensor(dofs, device="cuda")] = 1.0
+    vals_g = torch.zeros_like(mask)
+    v_elim, _ = _assemble_values(token, ebc, maps, ud, mask, vals_g, eliminate=True)
+    dw_o = orc.apply_dirichlet_bcs_lhs(d_o, r_o, c_o, dofs)
+    assert rel_err(v_elim, dw_o) <= ASM_RTOL
+    assert np.array_equal(np_(v_elim) == 1.0, dw_o == 1.0) and np.array_equal(np_(v_elim) == 0.0, dw_o == 0.0)
+    # bitwise reproducible
+    assert torch.equal(v_fused, _assemble_values(token, ebc, maps, ud)[0])
