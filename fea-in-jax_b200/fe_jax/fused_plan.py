@@ -110,6 +110,8 @@ def _build(vertices: torch.Tensor, conn32: torch.Tensor, row_ind: torch.Tensor, 
     tile_item_ptr = torch.searchsorted(tile[perm].contiguous(), torch.arange(n_tiles + 1, device=dev)).to(torch.int32)
     tile_nodes = order.to(torch.int32)
     keep = [t.contiguous() for t in (tile_node_ptr, tile_nodes, tile_elem_ptr, tile_elems, tile_item_ptr, tile_items)]
+    if not vertices.is_cuda:        # host-side inspection only (tests): arrays without the kernel-side struct
+        return FusedPlan(None, keep, n_tiles, tn_cap, te_cap, dict(n_tiles=n_tiles, te_cap=te_cap))
     struct = _lib.FusedPlan(n_tiles=n_tiles, tn_cap=tn_cap, te_cap=te_cap, tile_node_ptr=_lib.ptr(keep[0]),
                             tile_nodes=_lib.ptr(keep[1]), tile_elem_ptr=_lib.ptr(keep[2]), tile_elems=_lib.ptr(keep[3]),
                             tile_item_ptr=_lib.ptr(keep[4]), tile_items=_lib.ptr(keep[5]))
