@@ -19,11 +19,15 @@
 
 namespace feb {
 
-constexpr int FUSED_N = 8, FUSED_Q = 8, FUSED_D = 3;
+constexpr int FUSED_N = 8, FUSED_Q = 8;
 constexpr int FUSED_MAXVAL = 8;          // threads per vertex = max incident slots handled
-constexpr int G_STRIDE = 26;             // doubles per (element, node) gradient record (24 used): 16-byte aligned,
-                                         // consecutive records start 20 banks apart
+constexpr int FUSED_MAXDEG = 32;         // neighbour blocks per vertex handled by one warp pass (hex8: 27)
+constexpr int G_STRIDE = 26;             // doubles per (element, node) gradient record (24 used): 16-byte aligned
+constexpr int EL_STRIDE = 8 * G_STRIDE + 2;   // doubles per element in G: records of consecutive elements are 4 banks apart
+constexpr int XS_STRIDE = 25;            // doubles per element coordinate record (24 used)
+constexpr int DPHI_STRIDE = 25;          // doubles per quadrature point in the basis table (24 used)
 constexpr int BLK_STRIDE = 73;           // doubles per (vertex, slot) block row in the staging area (72 used, odd)
+constexpr int PF = 3;                    // prefetch registers per thread: covers te_cap*8 <= PF*256 (te_cap <= 96)
 
 struct FusedSmem {
     int tn_cap, te_cap;
@@ -33,50 +37,105 @@ static inline FusedSmem fused_layout(int tn_cap, int te_cap) {
     FusedSmem L;
     L.tn_cap = tn_cap;
     L.te_cap = te_cap;
-    size_t g_doubles = (size_t)te_cap * FUSED_N * G_STRIDE + (size_t)te_cap * FUSED_Q;      // G + wdet
+    size_t g_doubles = (size_t)te_cap * EL_STRIDE + (size_t)te_cap * FUSED_Q;      // G + wdet
     size_t st_doubles = (size_t)tn_cap * FUSED_MAXVAL * BLK_STRIDE;
     size_t a = g_doubles > st_doubles ? g_doubles : st_doubles;
     a = (a + 1) & ~(size_t)1;
     L.off_stage = 0;
     L.off_xs = a * 8;
-    L.off_dphi = L.off_xs + (size_t)te_cap * 24 * 8;
-    L.off_lm = L.off_dphi + (size_t)FUSED_Q * 24 * 8;
+    L.off_dphi = L.off_xs + (size_t)te_cap * XS_STRIDE * 8;
+    L.off_lm = L.off_dphi + (size_t)FUSED_Q * DPHI_STRIDE * 8;
     L.off_ints = L.off_lm + (size_t)te_cap * 2 * 8;
-    // ints: conn_s[te*8] i32, p0[tn] i64 (first, 8-aligned), node[tn] i32, deg[tn] i32, val[tn] i32, rk[tn*8*8] u16
-    L.total = L.off_ints + (size_t)tn_cap * 8 + (size_t)te_cap * 8 * 4 + (size_t)tn_cap * 4 * 3 +
-              (size_t)tn_cap * 64 * 2 + 64;
+    L.off_ints = (L.off_ints + 15) & ~(size_t)15;
+    // p0[tn] i64 | tbl[tn*32] u64 (source byte table) | nbr[tn*32] i32 | node[tn], deg[tn], val[tn] i32 | flg[tn*32] u8
+    L.total = L.off_ints + (size_t)tn_cap * 8 + (size_t)tn_cap * FUSED_MAXDEG * 8 + (size_t)tn_cap * FUSED_MAXDEG * 4 +
+              (size_t)tn_cap * 4 * 3 + (size_t)tn_cap * FUSED_MAXDEG + 64;
     return L;
 }
+
+// Tile data that is fetched from global memory ahead of time (while the previous tile computes):
+// level 1 element ids, level 2 vertex ids, level 3 coordinates.
+struct TilePrefetch {
+    int32_t el[PF];
+    int32_t vtx[PF];
+    double x[PF][3];
+};
 
 template <bool ELIM>
 __global__ void __launch_bounds__(256, 1)
 k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const double* __restrict__ x_vd,
                  const unsigned long long* __restrict__ row_ind, const uint16_t* __restrict__ slot_rank,
                  const int64_t* __restrict__ nindptr, const int32_t* __restrict__ nindices,
-                 const double* __restrict__ mask, double* __restrict__ values) {
+                 const uint8_t* __restrict__ vflags, double* __restrict__ values) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* G = reinterpret_cast<double*>(smem_raw + L.off_stage);          // [le][n][G_STRIDE] : g[q][3]
-    double* wdet = G + (size_t)L.te_cap * FUSED_N * G_STRIDE;               // [le][q]
+    double* G = reinterpret_cast<double*>(smem_raw + L.off_stage);          // [le] EL_STRIDE : [n] G_STRIDE : g[q][3]
+    double* wdet = G + (size_t)L.te_cap * EL_STRIDE;                        // [le][q]
     double* stage = reinterpret_cast<double*>(smem_raw + L.off_stage);      // [a][k][BLK_STRIDE]  (aliases G)
-    double* xs = reinterpret_cast<double*>(smem_raw + L.off_xs);            // [le][n][3]
-    double* s_dphi = reinterpret_cast<double*>(smem_raw + L.off_dphi);      // [q][n][3]
+    double* xs = reinterpret_cast<double*>(smem_raw + L.off_xs);            // [le] XS_STRIDE : [n][3]
+    double* s_dphi = reinterpret_cast<double*>(smem_raw + L.off_dphi);      // [q] DPHI_STRIDE : [n][3]
     double* lm = reinterpret_cast<double*>(smem_raw + L.off_lm);            // [le][2] lambda, mu
     int64_t* p0_s = reinterpret_cast<int64_t*>(smem_raw + L.off_ints);      // [a]
-    int32_t* conn_s = reinterpret_cast<int32_t*>(p0_s + L.tn_cap);          // [le][8]
-    int32_t* node_s = conn_s + (size_t)L.te_cap * 8;                        // [a]
+    unsigned long long* tbl = reinterpret_cast<unsigned long long*>(p0_s + L.tn_cap);   // [a][r]: byte k = local node b or 0xff
+    int32_t* nbr_s = reinterpret_cast<int32_t*>(tbl + (size_t)L.tn_cap * FUSED_MAXDEG);  // [a][r] neighbour vertex
+    int32_t* node_s = nbr_s + (size_t)L.tn_cap * FUSED_MAXDEG;              // [a]
     int32_t* deg_s = node_s + L.tn_cap;
     int32_t* val_s = deg_s + L.tn_cap;
-    uint16_t* rk_s = reinterpret_cast<uint16_t*>(val_s + L.tn_cap);         // [a][k][8]
+    uint8_t* flg_s = reinterpret_cast<uint8_t*>(val_s + L.tn_cap);          // [a][r] constrained components of the neighbour
 
     const int tid = threadIdx.x, nthr = blockDim.x;
-    for (int i = tid; i < FUSED_Q * 24; i += nthr) s_dphi[i] = b.dphi[i];
+    for (int i = tid; i < FUSED_Q * 24; i += nthr) s_dphi[(i / 24) * DPHI_STRIDE + (i % 24)] = b.dphi[i];
 
-    for (int tile = blockIdx.x; tile < plan.n_tiles; tile += gridDim.x) {
+    // ---- software pipeline over tiles: the (element -> vertex -> coordinate) gathers of the NEXT tile are issued
+    //      while the current tile computes
+    TilePrefetch pf;
+    auto pf_level1 = [&](int tile) {
+        const int e0 = plan.tile_elem_ptr[tile], TE = plan.tile_elem_ptr[tile + 1] - e0;
+#pragma unroll
+        for (int j = 0; j < PF; ++j) {
+            const int i = tid + j * 256;
+            pf.el[j] = (i < TE * 8) ? plan.tile_elems[e0 + (i >> 3)] : -1;
+        }
+    };
+    auto pf_level2 = [&]() {
+#pragma unroll
+        for (int j = 0; j < PF; ++j) pf.vtx[j] = (pf.el[j] >= 0) ? b.conn[(int64_t)pf.el[j] * 8 + ((tid + j * 256) & 7)] : -1;
+    };
+    auto pf_level3 = [&]() {
+#pragma unroll
+        for (int j = 0; j < PF; ++j)
+            if (pf.vtx[j] >= 0) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) pf.x[j][d] = x_vd[(int64_t)pf.vtx[j] * 3 + d];
+            }
+    };
+    int tile = blockIdx.x;
+    if (tile < plan.n_tiles) { pf_level1(tile); pf_level2(); pf_level3(); }
+
+    for (; tile < plan.n_tiles; tile += gridDim.x) {
         const int n0 = plan.tile_node_ptr[tile], TN = plan.tile_node_ptr[tile + 1] - n0;
         const int e0 = plan.tile_elem_ptr[tile], TE = plan.tile_elem_ptr[tile + 1] - e0;
         const int i0 = plan.tile_item_ptr[tile], NI = plan.tile_item_ptr[tile + 1] - i0;
+        const int next = tile + gridDim.x;
+        const bool has_next = next < plan.n_tiles;
         __syncthreads();                                     // previous tile fully consumed
-        // ---- P0: tile metadata, connectivity, coordinates
+        // ---- P0: prefetched coordinates -> smem; per-vertex metadata; neighbour lists and constraint flags
+#pragma unroll
+        for (int j = 0; j < PF; ++j) {
+            const int i = tid + j * 256;
+            if (i < TE * 8) {
+                const int le = i >> 3, n = i & 7;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) xs[le * XS_STRIDE + n * 3 + d] = pf.x[j][d];
+                if (n == 0) {
+                    int qs;
+                    const double* mp = mp_of(b, pf.el[j], qs);
+                    double lam, mu;
+                    isotropic_lame<3>(mp, lam, mu);
+                    lm[le * 2] = lam;
+                    lm[le * 2 + 1] = mu;
+                }
+            }
+        }
         for (int a = tid; a < TN; a += nthr) {
             const int node = plan.tile_nodes[n0 + a];
             node_s[a] = node;
@@ -85,34 +144,29 @@ k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const doub
             deg_s[a] = (int)(nindptr[node + 1] - p0);
             val_s[a] = (int)(row_ind[node + 1] - row_ind[node]);
         }
-        for (int i = tid; i < TE * 8; i += nthr) {
-            const int le = i >> 3, n = i & 7;
-            const int64_t e = plan.tile_elems[e0 + le];
-            const int32_t v = b.conn[e * 8 + n];
-            conn_s[i] = v;
-#pragma unroll
-            for (int d = 0; d < 3; ++d) xs[i * 3 + d] = x_vd[(int64_t)v * 3 + d];
-            if (n == 0) {
-                int qs;
-                const double* mp = mp_of(b, e, qs);
-                double lam, mu;
-                isotropic_lame<3>(mp, lam, mu);
-                lm[le * 2] = lam;
-                lm[le * 2 + 1] = mu;
+        for (int i = tid; i < TN * FUSED_MAXDEG; i += nthr) tbl[i] = ~0ull;
+        if (has_next) pf_level1(next);
+        __syncthreads();
+        for (int i = tid; i < TN * FUSED_MAXDEG; i += nthr) {          // neighbour ids + flags (consumed in P4)
+            const int a = i / FUSED_MAXDEG, r = i - a * FUSED_MAXDEG;
+            if (r < deg_s[a]) {
+                const int32_t nb = nindices[p0_s[a] + r];
+                nbr_s[i] = nb;
+                if (ELIM) flg_s[i] = vflags[nb];
             }
         }
-        __syncthreads();
         // ---- P1: geometry, one thread per (element, quadrature point)
         for (int i = tid; i < TE * 8; i += nthr) {
             const int le = i >> 3, q = i & 7;
             double g[24];
-            const double dt = shape_gradients<8, 3>(xs + le * 24, s_dphi + q * 24, g);
+            const double dt = shape_gradients<8, 3>(xs + le * XS_STRIDE, s_dphi + q * DPHI_STRIDE, g);
             wdet[i] = dt * b.W[q];
 #pragma unroll
             for (int n = 0; n < 8; ++n)
 #pragma unroll
-                for (int d = 0; d < 3; ++d) G[(size_t)(le * 8 + n) * G_STRIDE + q * 3 + d] = g[n * 3 + d];
+                for (int d = 0; d < 3; ++d) G[(size_t)le * EL_STRIDE + n * G_STRIDE + q * 3 + d] = g[n * 3 + d];
         }
+        if (has_next) pf_level2();
         __syncthreads();
         // ---- P2: block rows, one thread per (vertex, incident slot); items are sorted by element so that the
         //          lanes of a warp read few distinct gradient records (broadcast)
@@ -125,12 +179,18 @@ k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const doub
             a_loc = (it >> 16) & 0xff;
             kk = (it >> 24) & 0xff;
             const int64_t slot = (int64_t)plan.tile_elems[e0 + le] * 8 + na;
-            // ranks of the 8 neighbours of this slot: one 16-byte load
+            // ranks of the 8 local nodes of this slot (one 16-byte load) -> source table: tbl[a][rank] byte k = b
             const uint4 rk8 = *reinterpret_cast<const uint4*>(slot_rank + slot * 8);
-            *reinterpret_cast<uint4*>(rk_s + (size_t)(a_loc * FUSED_MAXVAL + kk) * 8) = rk8;
+            const unsigned int w4[4] = {rk8.x, rk8.y, rk8.z, rk8.w};
+            uint8_t* tb = reinterpret_cast<uint8_t*>(tbl + (size_t)a_loc * FUSED_MAXDEG);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                tb[(w4[j] & 0xffffu) * 8 + kk] = (uint8_t)(2 * j);
+                tb[(w4[j] >> 16) * 8 + kk] = (uint8_t)(2 * j + 1);
+            }
             double wga[8][3];
             {
-                const double2* rec = reinterpret_cast<const double2*>(G + (size_t)(le * 8 + na) * G_STRIDE);
+                const double2* rec = reinterpret_cast<const double2*>(G + (size_t)le * EL_STRIDE + na * G_STRIDE);
                 double tmp[24];
 #pragma unroll
                 for (int j = 0; j < 12; ++j) { const double2 v = rec[j]; tmp[2 * j] = v.x; tmp[2 * j + 1] = v.y; }
@@ -143,7 +203,7 @@ k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const doub
             const double lam = lm[le * 2], mu = lm[le * 2 + 1];
 #pragma unroll
             for (int bn = 0; bn < 8; ++bn) {
-                const double2* rec = reinterpret_cast<const double2*>(G + (size_t)(le * 8 + bn) * G_STRIDE);
+                const double2* rec = reinterpret_cast<const double2*>(G + (size_t)le * EL_STRIDE + bn * G_STRIDE);
                 double S[9];
 #pragma unroll
                 for (int c = 0; c < 9; ++c) S[c] = 0.0;
@@ -167,6 +227,7 @@ k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const doub
                         blk[bn][d * 3 + k] = lam * S[d * 3 + k] + mu * S[k * 3 + d] + (d == k ? tr : 0.0);
             }
         }
+        if (has_next) pf_level3();
         __syncthreads();                                     // all gradient reads done: staging may overwrite them
         // ---- P3: block rows to shared memory
         if (has_item) {
@@ -180,40 +241,40 @@ k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const doub
         // ---- P4: one warp per vertex, one lane per neighbour block; contributions added in ascending slot order
         const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
         for (int a = warp; a < TN; a += nwarp) {
-            const int deg = deg_s[a], val = val_s[a];
+            const int deg = deg_s[a];
             const int64_t node = node_s[a], p0 = p0_s[a];
             const int row_len = 3 * deg;
-            for (int r = lane; r < deg; r += 32) {
+            if (lane < deg) {
+                const int r = lane;
                 double acc[9];
 #pragma unroll
                 for (int c = 0; c < 9; ++c) acc[c] = 0.0;
-                for (int k = 0; k < val; ++k) {
-                    const uint4 rk8 = *reinterpret_cast<const uint4*>(rk_s + (size_t)(a * FUSED_MAXVAL + k) * 8);
-                    const unsigned int w4[4] = {rk8.x, rk8.y, rk8.z, rk8.w};
-                    int bsel = -1;
+                unsigned long long src = tbl[a * FUSED_MAXDEG + r];
+                const double* base = stage + (size_t)a * FUSED_MAXVAL * BLK_STRIDE;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if ((int)(w4[j] & 0xffffu) == r) bsel = 2 * j;
-                        if ((int)(w4[j] >> 16) == r) bsel = 2 * j + 1;
+                for (int k = 0; k < FUSED_MAXVAL; ++k) {
+                    const unsigned int bsel = (unsigned int)(src & 0xffull);
+                    src >>= 8;
+                    if (bsel != 0xffu) {
+                        const double* sp = base + k * BLK_STRIDE + bsel * 9;
+#pragma unroll
+                        for (int c = 0; c < 9; ++c) acc[c] += sp[c];
                     }
-                    if (bsel >= 0) {
-                        const double* src = stage + (size_t)(a * FUSED_MAXVAL + k) * BLK_STRIDE + bsel * 9;
+                }
+                if (ELIM) {
+                    const int32_t colv = nbr_s[a * FUSED_MAXDEG + r];
+                    const unsigned int cf = flg_s[a * FUSED_MAXDEG + r];
+                    const unsigned int rf = vflags[node];
+                    if (cf | rf) {
 #pragma unroll
-                        for (int c = 0; c < 9; ++c) acc[c] += src[c];
+                        for (int i = 0; i < 3; ++i)
+#pragma unroll
+                            for (int j = 0; j < 3; ++j)
+                                if (((rf >> i) & 1u) || ((cf >> j) & 1u))
+                                    acc[i * 3 + j] = (((rf >> i) & 1u) && colv == node && i == j) ? 1.0 : 0.0;
                     }
                 }
                 double* dst = values + 9 * p0 + 3 * r;
-                if (ELIM) {
-                    const int64_t colv = nindices[p0 + r];
-                    bool cm[3], rm[3];
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) { cm[j] = mask[colv * 3 + j] != 0.0; rm[j] = mask[node * 3 + j] != 0.0; }
-#pragma unroll
-                    for (int i = 0; i < 3; ++i)
-#pragma unroll
-                        for (int j = 0; j < 3; ++j)
-                            if (rm[i] || cm[j]) acc[i * 3 + j] = (rm[i] && colv == node && i == j) ? 1.0 : 0.0;
-                }
 #pragma unroll
                 for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -233,7 +294,7 @@ size_t feb200_fused_smem_bytes(int32_t tn_cap, int32_t te_cap) { return fused_la
 
 int feb200_assemble_fused_hex8(feb200_stream s, const feb200_batch* bp, const feb200_fused_plan* plan, const double* x_vd,
                                const uint64_t* row_ind, const uint16_t* slot_rank, const int64_t* nindptr,
-                               const int32_t* nindices, const double* mask, double* values) {
+                               const int32_t* nindices, const uint8_t* vertex_flags, double* values) {
     FEB_REQUIRE(bp && plan && x_vd && row_ind && slot_rank && nindptr && nindices && values, FEB200_ERR_INVALID,
                 "assemble_fused_hex8: null pointer");
     const feb200_batch& b = *bp;
@@ -245,7 +306,7 @@ int feb200_assemble_fused_hex8(feb200_stream s, const feb200_batch* bp, const fe
                     plan->tile_items && plan->n_tiles >= 0,
                 FEB200_ERR_INVALID, "assemble_fused_hex8: bad plan");
     FEB_REQUIRE(plan->tn_cap > 0 && plan->tn_cap % 4 == 0 && plan->tn_cap * FUSED_MAXVAL <= 256 && plan->te_cap > 0 &&
-                    plan->te_cap < 4096,
+                    plan->te_cap * 8 <= PF * 256,
                 FEB200_ERR_INVALID, "assemble_fused_hex8: plan capacities tn=%d te=%d out of range", plan->tn_cap, plan->te_cap);
     if (plan->n_tiles == 0) return FEB200_OK;
     const FusedSmem L = fused_layout(plan->tn_cap, plan->te_cap);
@@ -253,14 +314,14 @@ int feb200_assemble_fused_hex8(feb200_stream s, const feb200_batch* bp, const fe
     cudaStream_t st = as_stream(s);
     const unsigned long long* ri = reinterpret_cast<const unsigned long long*>(row_ind);
     int grid = plan->n_tiles < sm_count() ? plan->n_tiles : sm_count();
-    if (mask) {
+    if (vertex_flags) {
         auto kern = k_fused_hex8_iso<true>;
         FEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-        kern<<<grid, 256, L.total, st>>>(b, *plan, L, x_vd, ri, slot_rank, nindptr, nindices, mask, values);
+        kern<<<grid, 256, L.total, st>>>(b, *plan, L, x_vd, ri, slot_rank, nindptr, nindices, vertex_flags, values);
     } else {
         auto kern = k_fused_hex8_iso<false>;
         FEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-        kern<<<grid, 256, L.total, st>>>(b, *plan, L, x_vd, ri, slot_rank, nindptr, nindices, mask, values);
+        kern<<<grid, 256, L.total, st>>>(b, *plan, L, x_vd, ri, slot_rank, nindptr, nindices, vertex_flags, values);
     }
     FEB_CHECK_LAUNCH("assemble_fused_hex8");
     return FEB200_OK;

@@ -289,7 +289,7 @@ class _Plan:
         if i not in self._fused:
             plan = None
             if (os.environ.get("FEB200_FUSED", "1") != "0" and ebc.B == 1 and ebc.N[i] == 8 and ebc.Q[i] == 8
-                    and ebc.D == 3):
+                    and ebc.D == 3 and self.pattern.max_deg <= 32):
                 from .fused_plan import build_fused_plan
                 row, col = self._keep[i]
                 plan = build_fused_plan(ebc._vertices, ebc._conn32[i], row, col)
@@ -382,10 +382,10 @@ def _assemble_values(element_residual_func, ebc, assembly_map_b, u, mask=None, v
         if (b.kind == _lib.KIND_LINEAR and b.material == _lib.MAT_ISOTROPIC and b.layout != _lib.LAYOUT_EQM
                 and plan.fused_plan(ebc, i) is not None):
             fp = plan.fused_plan(ebc, i)
-            elim = eliminate and mask is not None
+            flags = _vertex_flags(ebc, mask) if (eliminate and mask is not None) else None
             _lib.call("feb200_assemble_fused_hex8", b, fp.struct, _lib.ptr(ebc._vertices), _lib.ptr(plan._keep[i][0]),
                       _lib.ptr(plan.slot_rank[i]), _lib.ptr(pat.nindptr), _lib.ptr(pat.nindices),
-                      _lib.ptr(mask) if elim else None, _lib.ptr(vals))
+                      _lib.ptr(flags), _lib.ptr(vals))
             continue
         K_e = ebc._buffer("K_e", ebc.E[i] * ebc.N[i] * ebc.N[i] * ebc.U[i] * ebc.U[i])
         _lib.call("feb200_element_tangent", b, _lib.ptr(ebc._vertices), _lib.ptr(u), _lib.ptr(mask), _lib.ptr(values),
@@ -396,6 +396,20 @@ def _assemble_values(element_residual_func, ebc, assembly_map_b, u, mask=None, v
                   _lib.ptr(pat.nindptr), pat.max_deg, _lib.ptr(vals), 1 if i > 0 else 0,
                   _lib.ptr(pat.nindices) if elim else None, _lib.ptr(mask) if elim else None)
     return vals, pat
+
+
+def _vertex_flags(ebc, mask):
+    """uint8 per vertex, bit j set when DoF U*v+j is constrained (input of the fused Dirichlet elimination);
+    cached per mask tensor."""
+    key = ("_vflags", mask.data_ptr(), mask._version)
+    hit = ebc._scratch.get("_vflags")
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    U = ebc.U[0]
+    bits = torch.tensor([1 << j for j in range(U)], dtype=torch.int32, device=mask.device)
+    flags = ((mask.view(-1, U) != 0).to(torch.int32) * bits).sum(dim=1).to(torch.uint8).contiguous()
+    ebc._scratch["_vflags"] = (key, flags)
+    return flags
 
 
 def calculate_jacobian_wo_dirichlet(element_residual_func, ebc: ElementBatchCollection, assembly_map_b, u_f,

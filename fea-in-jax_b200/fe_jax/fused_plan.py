@@ -36,7 +36,10 @@ def morton_codes(vertices: torch.Tensor) -> torch.Tensor:
     ext = torch.clamp(hi - lo, min=1e-300)
     vol = float(torch.prod(ext).item())
     cell = (vol / max(V, 1)) ** (1.0 / D)
-    q = torch.floor((vertices - lo) / cell + 0.5).to(torch.int64).clamp_(0, (1 << 21) - 1)
+    # vertices per axis ~ ext / cell; spacing = ext / (count - 1), exact for uniform grids (jitter < half a cell)
+    counts = torch.clamp(torch.round(ext / cell), min=2.0)
+    spacing = ext / (counts - 1.0)
+    q = torch.floor((vertices - lo) / spacing + 0.5).to(torch.int64).clamp_(0, (1 << 21) - 1)
     code = torch.zeros(V, dtype=torch.int64, device=vertices.device)
     for d in range(D):
         code |= _spread3(q[:, d]) << d
@@ -102,7 +105,7 @@ def _build(vertices: torch.Tensor, conn32: torch.Tensor, row_ind: torch.Tensor, 
     tile_elem_ptr = torch.searchsorted(tile_of_u, torch.arange(n_tiles + 1, device=dev)).to(torch.int32)
     te_cap = int((tile_elem_ptr[1:] - tile_elem_ptr[:-1]).max().item())
     le = inverse - tile_elem_ptr[tile].to(torch.int64)
-    if te_cap >= 4096 or int(lib.feb200_fused_smem_bytes(tn_cap, te_cap)) > SMEM_LIMIT:
+    if te_cap > 96 or int(lib.feb200_fused_smem_bytes(tn_cap, te_cap)) > SMEM_LIMIT:
         return None
     packed = (le | (n_a << 12) | (a_loc_of_node[node_of_entry] << 16) | (k_of_entry << 24))
     perm = torch.argsort(inverse * N + n_a, stable=True)           # tile-major, then element, then local node

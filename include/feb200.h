@@ -154,7 +154,9 @@ int feb200_assemble_csr(feb200_stream s, const feb200_batch_map* map, int64_t V,
  * vertices that are close in space; per tile: its vertices, the elements touching them and one packed item per
  * (vertex, incident slot): le | n_a << 12 | a_local << 16 | k << 24, sorted by (le, n_a).  Built by
  * fe_jax/fused_plan.py for any connectivity with vertex valence <= 8.  values are overwritten (single batch);
- * mask != NULL fuses apply_dirichlet_bcs_lhs.  Same summation order as feb200_assemble_csr. */
+ * vertex_flags != NULL fuses apply_dirichlet_bcs_lhs: one byte per vertex, bit j set when DoF 3*v+j is
+ * constrained.  Vertices may have at most 8 incident slots and 32 neighbours; te_cap <= 96.
+ * Same summation order as feb200_assemble_csr. */
 typedef struct {
     int32_t n_tiles;
     int32_t tn_cap;               /* max vertices per tile (multiple of 4, <= 32) */
@@ -170,7 +172,7 @@ typedef struct {
 size_t feb200_fused_smem_bytes(int32_t tn_cap, int32_t te_cap);
 int feb200_assemble_fused_hex8(feb200_stream s, const feb200_batch* b, const feb200_fused_plan* plan, const double* x_vd,
                                const uint64_t* row_ind, const uint16_t* slot_rank, const int64_t* nindptr,
-                               const int32_t* nindices, const double* mask, double* values);
+                               const int32_t* nindices, const uint8_t* vertex_flags, double* values);
 
 /* apply_dirichlet_bcs_lhs on the node-pattern CSR (sparse_matrix.py:157-184). mask: (U*V) 0/1 doubles. */
 int feb200_dirichlet_lhs(feb200_stream s, int64_t V, int32_t U, const int64_t* nindptr, const int32_t* nindices,
