@@ -19,15 +19,17 @@
 
 namespace feb {
 
-constexpr int FUSED_N = 8, FUSED_Q = 8;
+constexpr int FUSED_Q = 8;
 constexpr int FUSED_MAXVAL = 8;          // threads per vertex = max incident slots handled
-constexpr int FUSED_MAXDEG = 32;         // neighbour blocks per vertex handled by one warp pass (hex8: 27)
+constexpr int FUSED_MAXDEG = 32;         // neighbour blocks per vertex (one lane each; hex8: 27)
+constexpr int FUSED_THREADS = 256;
 constexpr int G_STRIDE = 26;             // doubles per (element, node) gradient record (24 used): 16-byte aligned
 constexpr int EL_STRIDE = 8 * G_STRIDE + 2;   // doubles per element in G: records of consecutive elements are 4 banks apart
 constexpr int XS_STRIDE = 25;            // doubles per element coordinate record (24 used)
 constexpr int DPHI_STRIDE = 25;          // doubles per quadrature point in the basis table (24 used)
-constexpr int BLK_STRIDE = 73;           // doubles per (vertex, slot) block row in the staging area (72 used, odd)
-constexpr int PF = 3;                    // prefetch registers per thread: covers te_cap*8 <= PF*256 (te_cap <= 96)
+constexpr int BLK_STRIDE = 73;           // doubles per item block row in the staging area (72 used, odd: conflict-free)
+constexpr int PF = 3;                    // element-node prefetch registers per thread: te_cap*8 <= PF*256 (te_cap <= 96)
+constexpr int PN = FUSED_MAXDEG * 32 / FUSED_THREADS;   // neighbour-table entries per thread (tn_cap <= 32)
 
 struct FusedSmem {
     int tn_cap, te_cap;
@@ -38,7 +40,7 @@ static inline FusedSmem fused_layout(int tn_cap, int te_cap) {
     L.tn_cap = tn_cap;
     L.te_cap = te_cap;
     size_t g_doubles = (size_t)te_cap * EL_STRIDE + (size_t)te_cap * FUSED_Q;      // G + wdet
-    size_t st_doubles = (size_t)tn_cap * FUSED_MAXVAL * BLK_STRIDE;
+    size_t st_doubles = (size_t)FUSED_THREADS * BLK_STRIDE;
     size_t a = g_doubles > st_doubles ? g_doubles : st_doubles;
     a = (a + 1) & ~(size_t)1;
     L.off_stage = 0;
@@ -47,81 +49,124 @@ static inline FusedSmem fused_layout(int tn_cap, int te_cap) {
     L.off_lm = L.off_dphi + (size_t)FUSED_Q * DPHI_STRIDE * 8;
     L.off_ints = L.off_lm + (size_t)te_cap * 2 * 8;
     L.off_ints = (L.off_ints + 15) & ~(size_t)15;
-    // p0[tn] i64 | tbl[tn*32] u64 (source byte table) | nbr[tn*32] i32 | node[tn], deg[tn], val[tn] i32 | flg[tn*32] u8
-    L.total = L.off_ints + (size_t)tn_cap * 8 + (size_t)tn_cap * FUSED_MAXDEG * 8 + (size_t)tn_cap * FUSED_MAXDEG * 4 +
-              (size_t)tn_cap * 4 * 3 + (size_t)tn_cap * FUSED_MAXDEG + 64;
+    // tbl[tn*32][8] u16 (source table, 16 B rows) | p0[tn] i64 | nbr[tn*32] i32 | node[tn], meta[tn] i32 | flg[tn*32] u8
+    L.total = L.off_ints + (size_t)tn_cap * FUSED_MAXDEG * 16 + (size_t)tn_cap * 8 + (size_t)tn_cap * FUSED_MAXDEG * 4 +
+              (size_t)tn_cap * 4 * 2 + (size_t)tn_cap * FUSED_MAXDEG + 64;
     return L;
 }
 
-// Tile data that is fetched from global memory ahead of time (while the previous tile computes):
-// level 1 element ids, level 2 vertex ids, level 3 coordinates.
+// Everything a tile reads from global memory is fetched one tile ahead, in three dependency levels that are issued
+// at different points of the previous tile's computation:
+//   A (plan arrays)          element ids, the thread's item word, vertex id / CSR offset / degree
+//   B (needs A)              vertex ids of the elements, neighbour vertex ids, element id of the item
+//   C (needs B)              coordinates, constraint flags of the neighbours, slot ranks of the item
 struct TilePrefetch {
-    int32_t el[PF];
-    int32_t vtx[PF];
-    double x[PF][3];
+    int32_t el[PF];          // A
+    uint32_t item;           // A
+    int32_t node, meta;      // A   (meta = degree | valence << 8), valid for tid < TN
+    int64_t p0;              // A
+    int64_t p0n[PN];         // A   CSR offset of the vertex owning neighbour-table entry tid + j*256
+    int32_t degn[PN];        // A
+    int32_t vtx[PF];         // B
+    int32_t nbr[PN];         // B
+    int32_t item_el;         // B
+    double x[PF][3];         // C
+    uint32_t flg;            // C   PN flags packed
+    uint4 rk8;               // C
 };
 
 template <bool ELIM>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(FUSED_THREADS, 1)
 k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const double* __restrict__ x_vd,
-                 const unsigned long long* __restrict__ row_ind, const uint16_t* __restrict__ slot_rank,
-                 const int64_t* __restrict__ nindptr, const int32_t* __restrict__ nindices,
+                 const uint16_t* __restrict__ slot_rank, const int32_t* __restrict__ nindices,
                  const uint8_t* __restrict__ vflags, double* __restrict__ values) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* G = reinterpret_cast<double*>(smem_raw + L.off_stage);          // [le] EL_STRIDE : [n] G_STRIDE : g[q][3]
     double* wdet = G + (size_t)L.te_cap * EL_STRIDE;                        // [le][q]
-    double* stage = reinterpret_cast<double*>(smem_raw + L.off_stage);      // [a][k][BLK_STRIDE]  (aliases G)
+    double* stage = reinterpret_cast<double*>(smem_raw + L.off_stage);      // [item] BLK_STRIDE  (aliases G)
     double* xs = reinterpret_cast<double*>(smem_raw + L.off_xs);            // [le] XS_STRIDE : [n][3]
     double* s_dphi = reinterpret_cast<double*>(smem_raw + L.off_dphi);      // [q] DPHI_STRIDE : [n][3]
     double* lm = reinterpret_cast<double*>(smem_raw + L.off_lm);            // [le][2] lambda, mu
-    int64_t* p0_s = reinterpret_cast<int64_t*>(smem_raw + L.off_ints);      // [a]
-    unsigned long long* tbl = reinterpret_cast<unsigned long long*>(p0_s + L.tn_cap);   // [a][r]: byte k = local node b or 0xff
-    int32_t* nbr_s = reinterpret_cast<int32_t*>(tbl + (size_t)L.tn_cap * FUSED_MAXDEG);  // [a][r] neighbour vertex
+    uint16_t* tbl = reinterpret_cast<uint16_t*>(smem_raw + L.off_ints);     // [a][r][k] = item << 3 | b, or 0xffff
+    int64_t* p0_s = reinterpret_cast<int64_t*>(tbl + (size_t)L.tn_cap * FUSED_MAXDEG * 8);   // [a]
+    int32_t* nbr_s = reinterpret_cast<int32_t*>(p0_s + L.tn_cap);           // [a][r] neighbour vertex
     int32_t* node_s = nbr_s + (size_t)L.tn_cap * FUSED_MAXDEG;              // [a]
-    int32_t* deg_s = node_s + L.tn_cap;
-    int32_t* val_s = deg_s + L.tn_cap;
-    uint8_t* flg_s = reinterpret_cast<uint8_t*>(val_s + L.tn_cap);          // [a][r] constrained components of the neighbour
+    int32_t* meta_s = node_s + L.tn_cap;                                    // [a] degree | valence << 8
+    uint8_t* flg_s = reinterpret_cast<uint8_t*>(meta_s + L.tn_cap);         // [a][r] constrained components of the neighbour
 
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    for (int i = tid; i < FUSED_Q * 24; i += nthr) s_dphi[(i / 24) * DPHI_STRIDE + (i % 24)] = b.dphi[i];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < FUSED_Q * 24; i += FUSED_THREADS) s_dphi[(i / 24) * DPHI_STRIDE + (i % 24)] = b.dphi[i];
 
-    // ---- software pipeline over tiles: the (element -> vertex -> coordinate) gathers of the NEXT tile are issued
-    //      while the current tile computes
     TilePrefetch pf;
-    auto pf_level1 = [&](int tile) {
+    auto level_a = [&](int tile) {
+        const int n0 = plan.tile_node_ptr[tile], TN = plan.tile_node_ptr[tile + 1] - n0;
         const int e0 = plan.tile_elem_ptr[tile], TE = plan.tile_elem_ptr[tile + 1] - e0;
+        const int i0 = plan.tile_item_ptr[tile], NI = plan.tile_item_ptr[tile + 1] - i0;
 #pragma unroll
         for (int j = 0; j < PF; ++j) {
-            const int i = tid + j * 256;
+            const int i = tid + j * FUSED_THREADS;
             pf.el[j] = (i < TE * 8) ? plan.tile_elems[e0 + (i >> 3)] : -1;
         }
-    };
-    auto pf_level2 = [&]() {
+        pf.item = (tid < NI) ? plan.tile_items[i0 + tid] : 0xffffffffu;
+        pf.node = -1;
+        if (tid < TN) {
+            pf.node = plan.tile_nodes[n0 + tid];
+            pf.meta = plan.tile_node_meta[n0 + tid];
+            pf.p0 = plan.tile_node_p0[n0 + tid];
+        }
 #pragma unroll
-        for (int j = 0; j < PF; ++j) pf.vtx[j] = (pf.el[j] >= 0) ? b.conn[(int64_t)pf.el[j] * 8 + ((tid + j * 256) & 7)] : -1;
+        for (int j = 0; j < PN; ++j) {
+            const int a = (tid + j * FUSED_THREADS) / FUSED_MAXDEG;
+            pf.degn[j] = 0;
+            if (a < TN) {
+                pf.p0n[j] = plan.tile_node_p0[n0 + a];
+                pf.degn[j] = plan.tile_node_meta[n0 + a] & 0xff;
+            }
+        }
     };
-    auto pf_level3 = [&]() {
+    auto level_b = [&](int tile) {
+        const int e0 = plan.tile_elem_ptr[tile];
+#pragma unroll
+        for (int j = 0; j < PF; ++j)
+            pf.vtx[j] = (pf.el[j] >= 0) ? b.conn[(int64_t)pf.el[j] * 8 + ((tid + j * FUSED_THREADS) & 7)] : -1;
+#pragma unroll
+        for (int j = 0; j < PN; ++j) {
+            const int r = (tid + j * FUSED_THREADS) % FUSED_MAXDEG;
+            pf.nbr[j] = (r < pf.degn[j]) ? nindices[pf.p0n[j] + r] : -1;
+        }
+        pf.item_el = (pf.item != 0xffffffffu) ? plan.tile_elems[e0 + (pf.item & 0xfff)] : -1;
+        if (ELIM && pf.node >= 0) pf.meta |= (int32_t)vflags[pf.node] << 16;      // constrained components of the row vertex
+    };
+    auto level_c = [&]() {
 #pragma unroll
         for (int j = 0; j < PF; ++j)
             if (pf.vtx[j] >= 0) {
 #pragma unroll
                 for (int d = 0; d < 3; ++d) pf.x[j][d] = x_vd[(int64_t)pf.vtx[j] * 3 + d];
             }
+        pf.flg = 0;
+        if (ELIM) {
+#pragma unroll
+            for (int j = 0; j < PN; ++j)
+                if (pf.nbr[j] >= 0) pf.flg |= (uint32_t)vflags[pf.nbr[j]] << (8 * j);
+        }
+        if (pf.item_el >= 0)
+            pf.rk8 = *reinterpret_cast<const uint4*>(slot_rank + ((int64_t)pf.item_el * 8 + ((pf.item >> 12) & 0xf)) * 8);
     };
+
     int tile = blockIdx.x;
-    if (tile < plan.n_tiles) { pf_level1(tile); pf_level2(); pf_level3(); }
+    if (tile < plan.n_tiles) { level_a(tile); level_b(tile); level_c(); }
 
     for (; tile < plan.n_tiles; tile += gridDim.x) {
-        const int n0 = plan.tile_node_ptr[tile], TN = plan.tile_node_ptr[tile + 1] - n0;
-        const int e0 = plan.tile_elem_ptr[tile], TE = plan.tile_elem_ptr[tile + 1] - e0;
-        const int i0 = plan.tile_item_ptr[tile], NI = plan.tile_item_ptr[tile + 1] - i0;
+        const int TN = plan.tile_node_ptr[tile + 1] - plan.tile_node_ptr[tile];
+        const int TE = plan.tile_elem_ptr[tile + 1] - plan.tile_elem_ptr[tile];
         const int next = tile + gridDim.x;
         const bool has_next = next < plan.n_tiles;
         __syncthreads();                                     // previous tile fully consumed
-        // ---- P0: prefetched coordinates -> smem; per-vertex metadata; neighbour lists and constraint flags
+        // ---- P0: prefetched data -> shared memory
 #pragma unroll
         for (int j = 0; j < PF; ++j) {
-            const int i = tid + j * 256;
+            const int i = tid + j * FUSED_THREADS;
             if (i < TE * 8) {
                 const int le = i >> 3, n = i & 7;
 #pragma unroll
@@ -136,27 +181,25 @@ k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const doub
                 }
             }
         }
-        for (int a = tid; a < TN; a += nthr) {
-            const int node = plan.tile_nodes[n0 + a];
-            node_s[a] = node;
-            const int64_t p0 = nindptr[node];
-            p0_s[a] = p0;
-            deg_s[a] = (int)(nindptr[node + 1] - p0);
-            val_s[a] = (int)(row_ind[node + 1] - row_ind[node]);
-        }
-        for (int i = tid; i < TN * FUSED_MAXDEG; i += nthr) tbl[i] = ~0ull;
-        if (has_next) pf_level1(next);
-        __syncthreads();
-        for (int i = tid; i < TN * FUSED_MAXDEG; i += nthr) {          // neighbour ids + flags (consumed in P4)
-            const int a = i / FUSED_MAXDEG, r = i - a * FUSED_MAXDEG;
-            if (r < deg_s[a]) {
-                const int32_t nb = nindices[p0_s[a] + r];
-                nbr_s[i] = nb;
-                if (ELIM) flg_s[i] = vflags[nb];
+        if (tid < TN) { node_s[tid] = pf.node; meta_s[tid] = pf.meta; p0_s[tid] = pf.p0; }
+#pragma unroll
+        for (int j = 0; j < PN; ++j) {
+            const int i = tid + j * FUSED_THREADS;
+            if (i < TN * FUSED_MAXDEG) {
+                nbr_s[i] = pf.nbr[j];
+                flg_s[i] = (uint8_t)((pf.flg >> (8 * j)) & 0xffu);
+                uint4 ff;
+                ff.x = ff.y = ff.z = ff.w = 0xffffffffu;
+                *reinterpret_cast<uint4*>(tbl + (size_t)i * 8) = ff;
             }
         }
+        // the item of this thread for this tile (registers), then start fetching the next tile
+        const uint32_t item = pf.item;
+        const uint4 rk8 = pf.rk8;
+        if (has_next) level_a(next);
+        __syncthreads();
         // ---- P1: geometry, one thread per (element, quadrature point)
-        for (int i = tid; i < TE * 8; i += nthr) {
+        for (int i = tid; i < TE * 8; i += FUSED_THREADS) {
             const int le = i >> 3, q = i & 7;
             double g[24];
             const double dt = shape_gradients<8, 3>(xs + le * XS_STRIDE, s_dphi + q * DPHI_STRIDE, g);
@@ -166,27 +209,21 @@ k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const doub
 #pragma unroll
                 for (int d = 0; d < 3; ++d) G[(size_t)le * EL_STRIDE + n * G_STRIDE + q * 3 + d] = g[n * 3 + d];
         }
-        if (has_next) pf_level2();
         __syncthreads();
         // ---- P2: block rows, one thread per (vertex, incident slot); items are sorted by element so that the
         //          lanes of a warp read few distinct gradient records (broadcast)
         double blk[8][9];
-        int a_loc = 0, kk = 0;
-        const bool has_item = tid < NI;
+        const bool has_item = item != 0xffffffffu;
         if (has_item) {
-            const uint32_t it = plan.tile_items[i0 + tid];
-            const int le = it & 0xfff, na = (it >> 12) & 0xf;
-            a_loc = (it >> 16) & 0xff;
-            kk = (it >> 24) & 0xff;
-            const int64_t slot = (int64_t)plan.tile_elems[e0 + le] * 8 + na;
-            // ranks of the 8 local nodes of this slot (one 16-byte load) -> source table: tbl[a][rank] byte k = b
-            const uint4 rk8 = *reinterpret_cast<const uint4*>(slot_rank + slot * 8);
+            const int le = item & 0xfff, na = (item >> 12) & 0xf;
+            const int a_loc = (item >> 16) & 0xff, kk = (item >> 24) & 0xff;
+            // source table: tbl[a][rank of local node b][k] = (this item << 3) | b
             const unsigned int w4[4] = {rk8.x, rk8.y, rk8.z, rk8.w};
-            uint8_t* tb = reinterpret_cast<uint8_t*>(tbl + (size_t)a_loc * FUSED_MAXDEG);
+            uint16_t* tb = tbl + (size_t)a_loc * FUSED_MAXDEG * 8 + kk;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                tb[(w4[j] & 0xffffu) * 8 + kk] = (uint8_t)(2 * j);
-                tb[(w4[j] >> 16) * 8 + kk] = (uint8_t)(2 * j + 1);
+                tb[(w4[j] & 0xffffu) * 8] = (uint16_t)((tid << 3) | (2 * j));
+                tb[(w4[j] >> 16) * 8] = (uint16_t)((tid << 3) | (2 * j + 1));
             }
             double wga[8][3];
             {
@@ -227,36 +264,36 @@ k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const doub
                         blk[bn][d * 3 + k] = lam * S[d * 3 + k] + mu * S[k * 3 + d] + (d == k ? tr : 0.0);
             }
         }
-        if (has_next) pf_level3();
+        if (has_next) level_b(next);
         __syncthreads();                                     // all gradient reads done: staging may overwrite them
-        // ---- P3: block rows to shared memory
+        // ---- P3: block rows to shared memory, indexed by item (conflict-free)
         if (has_item) {
-            double* dst = stage + (size_t)(a_loc * FUSED_MAXVAL + kk) * BLK_STRIDE;
+            double* dst = stage + (size_t)tid * BLK_STRIDE;
 #pragma unroll
             for (int bn = 0; bn < 8; ++bn)
 #pragma unroll
                 for (int c = 0; c < 9; ++c) dst[bn * 9 + c] = blk[bn][c];
         }
+        if (has_next) level_c();
         __syncthreads();
         // ---- P4: one warp per vertex, one lane per neighbour block; contributions added in ascending slot order
-        const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
-        for (int a = warp; a < TN; a += nwarp) {
-            const int deg = deg_s[a];
-            const int64_t node = node_s[a], p0 = p0_s[a];
-            const int row_len = 3 * deg;
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int a = warp; a < TN; a += FUSED_THREADS / 32) {
+            const int deg = meta_s[a] & 0xff;
             if (lane < deg) {
                 const int r = lane;
+                const int64_t node = node_s[a], p0 = p0_s[a];
+                const int row_len = 3 * deg;
                 double acc[9];
 #pragma unroll
                 for (int c = 0; c < 9; ++c) acc[c] = 0.0;
-                unsigned long long src = tbl[a * FUSED_MAXDEG + r];
-                const double* base = stage + (size_t)a * FUSED_MAXVAL * BLK_STRIDE;
+                const uint4 row = *reinterpret_cast<const uint4*>(tbl + (size_t)(a * FUSED_MAXDEG + r) * 8);
+                const unsigned int w4[4] = {row.x, row.y, row.z, row.w};
 #pragma unroll
                 for (int k = 0; k < FUSED_MAXVAL; ++k) {
-                    const unsigned int bsel = (unsigned int)(src & 0xffull);
-                    src >>= 8;
-                    if (bsel != 0xffu) {
-                        const double* sp = base + k * BLK_STRIDE + bsel * 9;
+                    const unsigned int ent = (k & 1) ? (w4[k >> 1] >> 16) : (w4[k >> 1] & 0xffffu);
+                    if (ent != 0xffffu) {
+                        const double* sp = stage + (size_t)(ent >> 3) * BLK_STRIDE + (ent & 7u) * 9;
 #pragma unroll
                         for (int c = 0; c < 9; ++c) acc[c] += sp[c];
                     }
@@ -264,7 +301,7 @@ k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const doub
                 if (ELIM) {
                     const int32_t colv = nbr_s[a * FUSED_MAXDEG + r];
                     const unsigned int cf = flg_s[a * FUSED_MAXDEG + r];
-                    const unsigned int rf = vflags[node];
+                    const unsigned int rf = ((unsigned int)meta_s[a] >> 16) & 7u;
                     if (cf | rf) {
 #pragma unroll
                         for (int i = 0; i < 3; ++i)
@@ -303,25 +340,26 @@ int feb200_assemble_fused_hex8(feb200_stream s, const feb200_batch* bp, const fe
                 FEB200_ERR_UNSUPPORTED, "assemble_fused_hex8: needs linear isotropic material, constant per element");
     FEB_REQUIRE(b.conn && b.dphi && b.W && b.mp && b.M >= 2, FEB200_ERR_INVALID, "assemble_fused_hex8: bad batch");
     FEB_REQUIRE(plan->tile_node_ptr && plan->tile_nodes && plan->tile_elem_ptr && plan->tile_elems && plan->tile_item_ptr &&
-                    plan->tile_items && plan->n_tiles >= 0,
+                    plan->tile_items && plan->tile_node_p0 && plan->tile_node_meta && plan->n_tiles >= 0,
                 FEB200_ERR_INVALID, "assemble_fused_hex8: bad plan");
-    FEB_REQUIRE(plan->tn_cap > 0 && plan->tn_cap % 4 == 0 && plan->tn_cap * FUSED_MAXVAL <= 256 && plan->te_cap > 0 &&
+    FEB_REQUIRE(plan->tn_cap > 0 && plan->tn_cap % 4 == 0 && plan->tn_cap <= 32 && plan->te_cap > 0 &&
                     plan->te_cap * 8 <= PF * 256,
                 FEB200_ERR_INVALID, "assemble_fused_hex8: plan capacities tn=%d te=%d out of range", plan->tn_cap, plan->te_cap);
     if (plan->n_tiles == 0) return FEB200_OK;
     const FusedSmem L = fused_layout(plan->tn_cap, plan->te_cap);
     FEB_REQUIRE(L.total <= 227 * 1024, FEB200_ERR_CAPACITY, "assemble_fused_hex8: tile needs %zu bytes of shared memory", L.total);
     cudaStream_t st = as_stream(s);
-    const unsigned long long* ri = reinterpret_cast<const unsigned long long*>(row_ind);
+    (void)row_ind;
+    (void)nindptr;
     int grid = plan->n_tiles < sm_count() ? plan->n_tiles : sm_count();
     if (vertex_flags) {
         auto kern = k_fused_hex8_iso<true>;
         FEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-        kern<<<grid, 256, L.total, st>>>(b, *plan, L, x_vd, ri, slot_rank, nindptr, nindices, vertex_flags, values);
+        kern<<<grid, FUSED_THREADS, L.total, st>>>(b, *plan, L, x_vd, slot_rank, nindices, vertex_flags, values);
     } else {
         auto kern = k_fused_hex8_iso<false>;
         FEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-        kern<<<grid, 256, L.total, st>>>(b, *plan, L, x_vd, ri, slot_rank, nindptr, nindices, vertex_flags, values);
+        kern<<<grid, FUSED_THREADS, L.total, st>>>(b, *plan, L, x_vd, slot_rank, nindices, vertex_flags, values);
     }
     FEB_CHECK_LAUNCH("assemble_fused_hex8");
     return FEB200_OK;

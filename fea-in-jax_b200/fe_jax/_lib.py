@@ -39,7 +39,8 @@ class BatchMap(Structure):
 class FusedPlan(Structure):
     _fields_ = [("n_tiles", c_int32), ("tn_cap", c_int32), ("te_cap", c_int32), ("reserved", c_int32),
                 ("tile_node_ptr", c_void_p), ("tile_nodes", c_void_p), ("tile_elem_ptr", c_void_p),
-                ("tile_elems", c_void_p), ("tile_item_ptr", c_void_p), ("tile_items", c_void_p)]
+                ("tile_elems", c_void_p), ("tile_item_ptr", c_void_p), ("tile_items", c_void_p),
+                ("tile_node_p0", c_void_p), ("tile_node_meta", c_void_p)]
 
 
 class CGState(Structure):

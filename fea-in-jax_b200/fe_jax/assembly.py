@@ -292,7 +292,7 @@ class _Plan:
                     and ebc.D == 3 and self.pattern.max_deg <= 32):
                 from .fused_plan import build_fused_plan
                 row, col = self._keep[i]
-                plan = build_fused_plan(ebc._vertices, ebc._conn32[i], row, col)
+                plan = build_fused_plan(ebc._vertices, ebc._conn32[i], row, col, self.pattern.nindptr)
             self._fused[i] = plan
         return self._fused[i]
 

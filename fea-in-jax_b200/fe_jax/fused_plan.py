@@ -52,17 +52,17 @@ class FusedPlan:
         self.n_tiles, self.tn_cap, self.te_cap, self.stats = n_tiles, tn_cap, te_cap, stats
 
 
-def build_fused_plan(vertices, conn32, row_ind, col_ind):
+def build_fused_plan(vertices, conn32, row_ind, col_ind, nindptr=None):
     """Largest tile size whose tiles fit in shared memory: 32 (4x4x2 Morton cells), else 16, else 8 vertices."""
     for tn_cap, shift in ((32, 5), (16, 4), (8, 3)):
-        plan = _build(vertices, conn32, row_ind, col_ind, tn_cap, shift)
+        plan = _build(vertices, conn32, row_ind, col_ind, tn_cap, shift, nindptr)
         if plan is not None:
             return plan
     return None
 
 
 def _build(vertices: torch.Tensor, conn32: torch.Tensor, row_ind: torch.Tensor, col_ind: torch.Tensor, tn_cap: int,
-           shift: int):
+           shift: int, nindptr=None):
     """vertices (V,3) f64, conn32 (E,8) i32, row_ind (V+1) / col_ind (E*8) int64 views of the assembly map."""
     lib = _lib.load()
     dev = vertices.device
@@ -115,9 +115,15 @@ def _build(vertices: torch.Tensor, conn32: torch.Tensor, row_ind: torch.Tensor, 
     keep = [t.contiguous() for t in (tile_node_ptr, tile_nodes, tile_elem_ptr, tile_elems, tile_item_ptr, tile_items)]
     if not vertices.is_cuda:        # host-side inspection only (tests): arrays without the kernel-side struct
         return FusedPlan(None, keep, n_tiles, tn_cap, te_cap, dict(n_tiles=n_tiles, te_cap=te_cap))
+    deg = nindptr[1:] - nindptr[:-1]
+    if int(deg.max().item()) > 32:
+        return None
+    keep.append(nindptr[:-1][order].contiguous())                                     # tile_node_p0
+    keep.append((deg[order] | (val[order] << 8)).to(torch.int32).contiguous())        # tile_node_meta
     struct = _lib.FusedPlan(n_tiles=n_tiles, tn_cap=tn_cap, te_cap=te_cap, tile_node_ptr=_lib.ptr(keep[0]),
                             tile_nodes=_lib.ptr(keep[1]), tile_elem_ptr=_lib.ptr(keep[2]), tile_elems=_lib.ptr(keep[3]),
-                            tile_item_ptr=_lib.ptr(keep[4]), tile_items=_lib.ptr(keep[5]))
+                            tile_item_ptr=_lib.ptr(keep[4]), tile_items=_lib.ptr(keep[5]),
+                            tile_node_p0=_lib.ptr(keep[6]), tile_node_meta=_lib.ptr(keep[7]))
     stats = dict(n_tiles=n_tiles, te_cap=te_cap, mean_nodes_per_tile=V / n_tiles,
                  element_visits_per_element=float(tile_elems.shape[0]) / E,
                  smem_bytes=int(lib.feb200_fused_smem_bytes(tn_cap, te_cap)))

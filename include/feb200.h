@@ -168,6 +168,8 @@ typedef struct {
     const int32_t* tile_elems;    /* element ids, ascending within a tile */
     const int32_t* tile_item_ptr; /* (n_tiles+1) */
     const uint32_t* tile_items;
+    const int64_t* tile_node_p0;  /* nindptr[vertex], parallel to tile_nodes */
+    const int32_t* tile_node_meta;/* degree | valence << 8, parallel to tile_nodes */
 } feb200_fused_plan;
 size_t feb200_fused_smem_bytes(int32_t tn_cap, int32_t te_cap);
 int feb200_assemble_fused_hex8(feb200_stream s, const feb200_batch* b, const feb200_fused_plan* plan, const double* x_vd,
