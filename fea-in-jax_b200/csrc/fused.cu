@@ -20,38 +20,41 @@
 namespace feb {
 
 constexpr int FUSED_Q = 8;
-constexpr int FUSED_MAXVAL = 8;          // threads per vertex = max incident slots handled
+constexpr int FUSED_MAXVAL = 8;          // incident slots per vertex handled (lane = 4*k + b/2)
 constexpr int FUSED_MAXDEG = 32;         // neighbour blocks per vertex (one lane each; hex8: 27)
-constexpr int FUSED_THREADS = 256;
+constexpr int FUSED_WARPS = 12;
+constexpr int FUSED_THREADS = FUSED_WARPS * 32;
 constexpr int G_STRIDE = 26;             // doubles per (element, node) gradient record (24 used): 16-byte aligned
 constexpr int EL_STRIDE = 8 * G_STRIDE + 2;   // doubles per element in G: records of consecutive elements are 4 banks apart
 constexpr int XS_STRIDE = 25;            // doubles per element coordinate record (24 used)
 constexpr int DPHI_STRIDE = 25;          // doubles per quadrature point in the basis table (24 used)
-constexpr int BLK_STRIDE = 73;           // doubles per item block row in the staging area (72 used, odd: conflict-free)
-constexpr int PF = 3;                    // element-node prefetch registers per thread: te_cap*8 <= PF*256 (te_cap <= 96)
-constexpr int PN = FUSED_MAXDEG * 32 / FUSED_THREADS;   // neighbour-table entries per thread (tn_cap <= 32)
+constexpr int WS_DOUBLES = FUSED_MAXVAL * 8 * 9;      // per-warp staging: block (k, b) at (k*8+b)*9
+constexpr int PF = 2;                    // element-node prefetch registers per thread: te_cap*8 <= PF*THREADS (te_cap <= 96)
+constexpr int PN = (FUSED_MAXDEG * 32 + FUSED_THREADS - 1) / FUSED_THREADS;   // neighbour-table entries per thread
 
 struct FusedSmem {
     int tn_cap, te_cap;
-    size_t off_stage, off_xs, off_dphi, off_lm, off_ints, total;
+    size_t off_g, off_ws, off_dphi, off_lm, off_ints, total;
 };
 static inline FusedSmem fused_layout(int tn_cap, int te_cap) {
     FusedSmem L;
     L.tn_cap = tn_cap;
     L.te_cap = te_cap;
+    L.off_g = 0;
     size_t g_doubles = (size_t)te_cap * EL_STRIDE + (size_t)te_cap * FUSED_Q;      // G + wdet
-    size_t st_doubles = (size_t)FUSED_THREADS * BLK_STRIDE;
-    size_t a = g_doubles > st_doubles ? g_doubles : st_doubles;
-    a = (a + 1) & ~(size_t)1;
-    L.off_stage = 0;
-    L.off_xs = a * 8;
-    L.off_dphi = L.off_xs + (size_t)te_cap * XS_STRIDE * 8;
+    g_doubles = (g_doubles + 1) & ~(size_t)1;
+    L.off_ws = g_doubles * 8;
+    size_t ws_doubles = (size_t)FUSED_WARPS * WS_DOUBLES;                          // xs (te*25) aliases the start
+    size_t xs_doubles = (size_t)te_cap * XS_STRIDE;
+    if (ws_doubles < xs_doubles) ws_doubles = xs_doubles;
+    ws_doubles = (ws_doubles + 1) & ~(size_t)1;
+    L.off_dphi = L.off_ws + ws_doubles * 8;
     L.off_lm = L.off_dphi + (size_t)FUSED_Q * DPHI_STRIDE * 8;
     L.off_ints = L.off_lm + (size_t)te_cap * 2 * 8;
     L.off_ints = (L.off_ints + 15) & ~(size_t)15;
-    // tbl[tn*32][8] u16 (source table, 16 B rows) | p0[tn] i64 | nbr[tn*32] i32 | node[tn], meta[tn] i32 | flg[tn*32] u8
-    L.total = L.off_ints + (size_t)tn_cap * FUSED_MAXDEG * 16 + (size_t)tn_cap * 8 + (size_t)tn_cap * FUSED_MAXDEG * 4 +
-              (size_t)tn_cap * 4 * 2 + (size_t)tn_cap * FUSED_MAXDEG + 64;
+    // tbl[tn*32] u64 | p0[tn] i64 | items[tn*8] u32 | nbr[tn*32] i32 | node[tn], meta[tn] i32 | flg[tn*32] u8
+    L.total = L.off_ints + (size_t)tn_cap * FUSED_MAXDEG * 8 + (size_t)tn_cap * 8 + (size_t)tn_cap * FUSED_MAXVAL * 4 +
+              (size_t)tn_cap * FUSED_MAXDEG * 4 + (size_t)tn_cap * 4 * 2 + (size_t)tn_cap * FUSED_MAXDEG + 64;
     return L;
 }
 
@@ -63,9 +66,9 @@ static inline FusedSmem fused_layout(int tn_cap, int te_cap) {
 struct TilePrefetch {
     int32_t el[PF];          // A
     uint32_t item;           // A
-    int32_t node, meta;      // A   (meta = degree | valence << 8), valid for tid < TN
+    int32_t node, meta;      // A   (meta = degree | valence << 8 | row flags << 16), valid for tid < TN
     int64_t p0;              // A
-    int64_t p0n[PN];         // A   CSR offset of the vertex owning neighbour-table entry tid + j*256
+    int64_t p0n[PN];         // A   CSR offset of the vertex owning neighbour-table entry tid + j*THREADS
     int32_t degn[PN];        // A
     int32_t vtx[PF];         // B
     int32_t nbr[PN];         // B
@@ -75,26 +78,30 @@ struct TilePrefetch {
     uint4 rk8;               // C
 };
 
+// P0/P1 are CTA-wide (one barrier each); after that every warp works alone on one vertex at a time:
+//   A  lane = 4*k + b/2 computes the two blocks K_e[a, b], K_e[a, b+1] of incident slot k  -> warp-private staging
+//   B  lane = neighbour rank r adds its <= 8 contributions in ascending slot order, eliminates, stores
 template <bool ELIM>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const double* __restrict__ x_vd,
                  const uint16_t* __restrict__ slot_rank, const int32_t* __restrict__ nindices,
                  const uint8_t* __restrict__ vflags, double* __restrict__ values) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* G = reinterpret_cast<double*>(smem_raw + L.off_stage);          // [le] EL_STRIDE : [n] G_STRIDE : g[q][3]
+    double* G = reinterpret_cast<double*>(smem_raw + L.off_g);              // [le] EL_STRIDE : [n] G_STRIDE : g[q][3]
     double* wdet = G + (size_t)L.te_cap * EL_STRIDE;                        // [le][q]
-    double* stage = reinterpret_cast<double*>(smem_raw + L.off_stage);      // [item] BLK_STRIDE  (aliases G)
-    double* xs = reinterpret_cast<double*>(smem_raw + L.off_xs);            // [le] XS_STRIDE : [n][3]
+    double* wstage = reinterpret_cast<double*>(smem_raw + L.off_ws);        // [warp][k][b][9]
+    double* xs = wstage;                                                    // [le] XS_STRIDE : [n][3]   (P0-P1 only)
     double* s_dphi = reinterpret_cast<double*>(smem_raw + L.off_dphi);      // [q] DPHI_STRIDE : [n][3]
     double* lm = reinterpret_cast<double*>(smem_raw + L.off_lm);            // [le][2] lambda, mu
-    uint16_t* tbl = reinterpret_cast<uint16_t*>(smem_raw + L.off_ints);     // [a][r][k] = item << 3 | b, or 0xffff
-    int64_t* p0_s = reinterpret_cast<int64_t*>(tbl + (size_t)L.tn_cap * FUSED_MAXDEG * 8);   // [a]
-    int32_t* nbr_s = reinterpret_cast<int32_t*>(p0_s + L.tn_cap);           // [a][r] neighbour vertex
+    unsigned long long* tbl = reinterpret_cast<unsigned long long*>(smem_raw + L.off_ints);  // [a][r]: byte k = b or 0xff
+    int64_t* p0_s = reinterpret_cast<int64_t*>(tbl + (size_t)L.tn_cap * FUSED_MAXDEG);       // [a]
+    uint32_t* items_s = reinterpret_cast<uint32_t*>(p0_s + L.tn_cap);       // [a][k] = le | na << 12
+    int32_t* nbr_s = reinterpret_cast<int32_t*>(items_s + (size_t)L.tn_cap * FUSED_MAXVAL);  // [a][r] neighbour vertex
     int32_t* node_s = nbr_s + (size_t)L.tn_cap * FUSED_MAXDEG;              // [a]
-    int32_t* meta_s = node_s + L.tn_cap;                                    // [a] degree | valence << 8
+    int32_t* meta_s = node_s + L.tn_cap;                                    // [a]
     uint8_t* flg_s = reinterpret_cast<uint8_t*>(meta_s + L.tn_cap);         // [a][r] constrained components of the neighbour
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < FUSED_Q * 24; i += FUSED_THREADS) s_dphi[(i / 24) * DPHI_STRIDE + (i % 24)] = b.dphi[i];
 
     TilePrefetch pf;
@@ -188,16 +195,24 @@ k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const doub
             if (i < TN * FUSED_MAXDEG) {
                 nbr_s[i] = pf.nbr[j];
                 flg_s[i] = (uint8_t)((pf.flg >> (8 * j)) & 0xffu);
-                uint4 ff;
-                ff.x = ff.y = ff.z = ff.w = 0xffffffffu;
-                *reinterpret_cast<uint4*>(tbl + (size_t)i * 8) = ff;
+                tbl[i] = ~0ull;
             }
         }
-        // the item of this thread for this tile (registers), then start fetching the next tile
         const uint32_t item = pf.item;
         const uint4 rk8 = pf.rk8;
+        if (item != 0xffffffffu) items_s[((item >> 16) & 0xff) * FUSED_MAXVAL + ((item >> 24) & 0xff)] = item & 0xffffu;
         if (has_next) level_a(next);
         __syncthreads();
+        // source table: tbl[a][rank of local node b] byte k = b   (items of this tile, after the table was cleared)
+        if (item != 0xffffffffu) {
+            const unsigned int w4[4] = {rk8.x, rk8.y, rk8.z, rk8.w};
+            uint8_t* tb = reinterpret_cast<uint8_t*>(tbl + (size_t)((item >> 16) & 0xff) * FUSED_MAXDEG) + ((item >> 24) & 0xff);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                tb[(w4[j] & 0xffffu) * 8] = (uint8_t)(2 * j);
+                tb[(w4[j] >> 16) * 8] = (uint8_t)(2 * j + 1);
+            }
+        }
         // ---- P1: geometry, one thread per (element, quadrature point)
         for (int i = tid; i < TE * 8; i += FUSED_THREADS) {
             const int le = i >> 3, q = i & 7;
@@ -209,77 +224,64 @@ k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const doub
 #pragma unroll
                 for (int d = 0; d < 3; ++d) G[(size_t)le * EL_STRIDE + n * G_STRIDE + q * 3 + d] = g[n * 3 + d];
         }
-        __syncthreads();
-        // ---- P2: block rows, one thread per (vertex, incident slot); items are sorted by element so that the
-        //          lanes of a warp read few distinct gradient records (broadcast)
-        double blk[8][9];
-        const bool has_item = item != 0xffffffffu;
-        if (has_item) {
-            const int le = item & 0xfff, na = (item >> 12) & 0xf;
-            const int a_loc = (item >> 16) & 0xff, kk = (item >> 24) & 0xff;
-            // source table: tbl[a][rank of local node b][k] = (this item << 3) | b
-            const unsigned int w4[4] = {rk8.x, rk8.y, rk8.z, rk8.w};
-            uint16_t* tb = tbl + (size_t)a_loc * FUSED_MAXDEG * 8 + kk;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                tb[(w4[j] & 0xffffu) * 8] = (uint16_t)((tid << 3) | (2 * j));
-                tb[(w4[j] >> 16) * 8] = (uint16_t)((tid << 3) | (2 * j + 1));
-            }
-            double wga[8][3];
-            {
-                const double2* rec = reinterpret_cast<const double2*>(G + (size_t)le * EL_STRIDE + na * G_STRIDE);
-                double tmp[24];
-#pragma unroll
-                for (int j = 0; j < 12; ++j) { const double2 v = rec[j]; tmp[2 * j] = v.x; tmp[2 * j + 1] = v.y; }
-                const double* w = wdet + le * 8;
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) wga[q][d] = w[q] * tmp[q * 3 + d];
-            }
-            const double lam = lm[le * 2], mu = lm[le * 2 + 1];
-#pragma unroll
-            for (int bn = 0; bn < 8; ++bn) {
-                const double2* rec = reinterpret_cast<const double2*>(G + (size_t)le * EL_STRIDE + bn * G_STRIDE);
-                double S[9];
-#pragma unroll
-                for (int c = 0; c < 9; ++c) S[c] = 0.0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {                  // 3 double2 = 6 doubles = 2 quadrature points
-                    const double2 v0 = rec[3 * j], v1 = rec[3 * j + 1], v2 = rec[3 * j + 2];
-                    const double gb0[3] = {v0.x, v0.y, v1.x}, gb1[3] = {v1.y, v2.x, v2.y};
-#pragma unroll
-                    for (int i = 0; i < 3; ++i)
-#pragma unroll
-                        for (int l = 0; l < 3; ++l) {
-                            S[i * 3 + l] += wga[2 * j][i] * gb0[l];
-                            S[i * 3 + l] += wga[2 * j + 1][i] * gb1[l];
-                        }
-                }
-                const double tr = mu * (S[0] + S[4] + S[8]);
-#pragma unroll
-                for (int d = 0; d < 3; ++d)
-#pragma unroll
-                    for (int k = 0; k < 3; ++k)
-                        blk[bn][d * 3 + k] = lam * S[d * 3 + k] + mu * S[k * 3 + d] + (d == k ? tr : 0.0);
-            }
-        }
         if (has_next) level_b(next);
-        __syncthreads();                                     // all gradient reads done: staging may overwrite them
-        // ---- P3: block rows to shared memory, indexed by item (conflict-free)
-        if (has_item) {
-            double* dst = stage + (size_t)tid * BLK_STRIDE;
+        __syncthreads();                                     // gradients complete; xs dead -> warp staging may be written
+        // ---- P2: every warp takes vertices a = warp, warp + WARPS, ...
+        double* ws = wstage + (size_t)warp * WS_DOUBLES;
+        bool fetched_c = false;
+        for (int a = warp; a < TN; a += FUSED_WARPS) {
+            const int meta = meta_s[a];
+            const int deg = meta & 0xff, val = (meta >> 8) & 0xff;
+            // A: lane = 4*k + b/2
+            {
+                const int k = lane >> 2, bp = lane & 3;
+                if (k < val) {
+                    const uint32_t itw = items_s[a * FUSED_MAXVAL + k];
+                    const int le = itw & 0xfff, na = (itw >> 12) & 0xf;
+                    double wga[8][3];
+                    {
+                        const double2* rec = reinterpret_cast<const double2*>(G + (size_t)le * EL_STRIDE + na * G_STRIDE);
+                        double tmp[24];
 #pragma unroll
-            for (int bn = 0; bn < 8; ++bn)
+                        for (int j = 0; j < 12; ++j) { const double2 v = rec[j]; tmp[2 * j] = v.x; tmp[2 * j + 1] = v.y; }
+                        const double* w = wdet + le * 8;
 #pragma unroll
-                for (int c = 0; c < 9; ++c) dst[bn * 9 + c] = blk[bn][c];
-        }
-        if (has_next) level_c();
-        __syncthreads();
-        // ---- P4: one warp per vertex, one lane per neighbour block; contributions added in ascending slot order
-        const int lane = tid & 31, warp = tid >> 5;
-        for (int a = warp; a < TN; a += FUSED_THREADS / 32) {
-            const int deg = meta_s[a] & 0xff;
+                        for (int q = 0; q < 8; ++q)
+#pragma unroll
+                            for (int d = 0; d < 3; ++d) wga[q][d] = w[q] * tmp[q * 3 + d];
+                    }
+                    const double lam = lm[le * 2], mu = lm[le * 2 + 1];
+#pragma unroll
+                    for (int bi = 0; bi < 2; ++bi) {
+                        const int bn = 2 * bp + bi;
+                        const double2* rec = reinterpret_cast<const double2*>(G + (size_t)le * EL_STRIDE + bn * G_STRIDE);
+                        double S[9];
+#pragma unroll
+                        for (int c = 0; c < 9; ++c) S[c] = 0.0;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {          // 3 double2 = 6 doubles = 2 quadrature points
+                            const double2 v0 = rec[3 * j], v1 = rec[3 * j + 1], v2 = rec[3 * j + 2];
+                            const double gb0[3] = {v0.x, v0.y, v1.x}, gb1[3] = {v1.y, v2.x, v2.y};
+#pragma unroll
+                            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                                for (int l = 0; l < 3; ++l) {
+                                    S[i * 3 + l] += wga[2 * j][i] * gb0[l];
+                                    S[i * 3 + l] += wga[2 * j + 1][i] * gb1[l];
+                                }
+                        }
+                        const double tr = mu * (S[0] + S[4] + S[8]);
+                        double* dst = ws + (k * 8 + bn) * 9;
+#pragma unroll
+                        for (int d = 0; d < 3; ++d)
+#pragma unroll
+                            for (int kk = 0; kk < 3; ++kk)
+                                dst[d * 3 + kk] = lam * S[d * 3 + kk] + mu * S[kk * 3 + d] + (d == kk ? tr : 0.0);
+                    }
+                }
+            }
+            __syncwarp();
+            // B: lane = neighbour rank
             if (lane < deg) {
                 const int r = lane;
                 const int64_t node = node_s[a], p0 = p0_s[a];
@@ -287,13 +289,13 @@ k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const doub
                 double acc[9];
 #pragma unroll
                 for (int c = 0; c < 9; ++c) acc[c] = 0.0;
-                const uint4 row = *reinterpret_cast<const uint4*>(tbl + (size_t)(a * FUSED_MAXDEG + r) * 8);
-                const unsigned int w4[4] = {row.x, row.y, row.z, row.w};
+                unsigned long long src = tbl[a * FUSED_MAXDEG + r];
 #pragma unroll
                 for (int k = 0; k < FUSED_MAXVAL; ++k) {
-                    const unsigned int ent = (k & 1) ? (w4[k >> 1] >> 16) : (w4[k >> 1] & 0xffffu);
-                    if (ent != 0xffffu) {
-                        const double* sp = stage + (size_t)(ent >> 3) * BLK_STRIDE + (ent & 7u) * 9;
+                    const unsigned int bsel = (unsigned int)(src & 0xffull);
+                    src >>= 8;
+                    if (bsel != 0xffu) {
+                        const double* sp = ws + (k * 8 + bsel) * 9;
 #pragma unroll
                         for (int c = 0; c < 9; ++c) acc[c] += sp[c];
                     }
@@ -301,7 +303,7 @@ k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const doub
                 if (ELIM) {
                     const int32_t colv = nbr_s[a * FUSED_MAXDEG + r];
                     const unsigned int cf = flg_s[a * FUSED_MAXDEG + r];
-                    const unsigned int rf = ((unsigned int)meta_s[a] >> 16) & 7u;
+                    const unsigned int rf = ((unsigned int)meta >> 16) & 7u;
                     if (cf | rf) {
 #pragma unroll
                         for (int i = 0; i < 3; ++i)
@@ -317,7 +319,10 @@ k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const doub
 #pragma unroll
                     for (int j = 0; j < 3; ++j) __stcs(dst + (int64_t)i * row_len + j, acc[i * 3 + j]);
             }
+            __syncwarp();
+            if (has_next && !fetched_c) { level_c(); fetched_c = true; }
         }
+        if (has_next && !fetched_c) level_c();
     }
 }
 
@@ -343,7 +348,7 @@ int feb200_assemble_fused_hex8(feb200_stream s, const feb200_batch* bp, const fe
                     plan->tile_items && plan->tile_node_p0 && plan->tile_node_meta && plan->n_tiles >= 0,
                 FEB200_ERR_INVALID, "assemble_fused_hex8: bad plan");
     FEB_REQUIRE(plan->tn_cap > 0 && plan->tn_cap % 4 == 0 && plan->tn_cap <= 32 && plan->te_cap > 0 &&
-                    plan->te_cap * 8 <= PF * 256,
+                    plan->te_cap * 8 <= PF * FUSED_THREADS && plan->tn_cap * FUSED_MAXVAL <= FUSED_THREADS,
                 FEB200_ERR_INVALID, "assemble_fused_hex8: plan capacities tn=%d te=%d out of range", plan->tn_cap, plan->te_cap);
     if (plan->n_tiles == 0) return FEB200_OK;
     const FusedSmem L = fused_layout(plan->tn_cap, plan->te_cap);
