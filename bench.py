@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--cpu-n", type=int, default=20, help="grid size of the bounded CPU-baseline sample")
     ap.add_argument("--layout", default="M", choices=["M", "EM", "EQM"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--two-pass", action="store_true", help="also time the generic two-pass assembly kernels")
     return ap.parse_args()
 
 
@@ -254,22 +255,30 @@ def main():
     # ---- per-kernel durations (same inputs, each kernel timed on its own over `steps` launches)
     res = fj.physics.resolve_residual(token)
     bstruct = ebc._batch_struct(0, res.kind)
-    K_e = ebc._buffer("K_e", E * 8 * 8 * 9)
     R_e = ebc._buffer("R_e", E * 24)
     Rtmp = torch.empty(F, dtype=torch.float64, device=dev)
     row = maps[0].indptr.reshape(-1).view(torch.int64)
     col = maps[0].indices.reshape(-1).view(torch.int64)
+    fused = plan.fused_plan(ebc, 0) if bstruct.layout != _lib.LAYOUT_EQM else None
+    from fe_jax.assembly import _vertex_flags
+    vflags = _vertex_flags(ebc, mask)
     kernels = {
         "element_residual": lambda: _lib.call("feb200_element_residual", bstruct, _lib.ptr(ebc._vertices), _lib.ptr(u),
                                               _lib.ptr(mask), _lib.ptr(values), _lib.ptr(R_e)),
         "scatter_sum": lambda: _lib.call("feb200_scatter_sum", _lib.ptr(row), _lib.ptr(col), V, 3, _lib.ptr(R_e),
                                          _lib.ptr(Rtmp), 0, _lib.ptr(mask), _lib.ptr(values), _lib.ptr(u)),
-        "element_tangent": lambda: _lib.call("feb200_element_tangent", bstruct, _lib.ptr(ebc._vertices), _lib.ptr(u),
-                                             _lib.ptr(mask), _lib.ptr(values), _lib.ptr(K_e)),
-        "assemble_csr": lambda: _lib.call("feb200_assemble_csr", plan.maps[0], pat.V, pat.U, _lib.ptr(K_e),
-                                          _lib.ptr(plan.slot_rank[0]), _lib.ptr(pat.nindptr), pat.max_deg,
-                                          _lib.ptr(J_vals), 0, _lib.ptr(pat.nindices), _lib.ptr(mask)),
     }
+    if fused is not None:
+        kernels["assemble_fused_hex8"] = lambda: _lib.call(
+            "feb200_assemble_fused_hex8", bstruct, fused.struct, _lib.ptr(ebc._vertices), _lib.ptr(row),
+            _lib.ptr(plan.slot_rank[0]), _lib.ptr(pat.nindptr), _lib.ptr(pat.nindices), _lib.ptr(vflags), _lib.ptr(J_vals))
+    if fused is None or args.two_pass:
+        K_e = ebc._buffer("K_e", E * 8 * 8 * 9)
+        kernels["element_tangent"] = lambda: _lib.call("feb200_element_tangent", bstruct, _lib.ptr(ebc._vertices), _lib.ptr(u),
+                                                       _lib.ptr(mask), _lib.ptr(values), _lib.ptr(K_e))
+        kernels["assemble_csr"] = lambda: _lib.call("feb200_assemble_csr", plan.maps[0], pat.V, pat.U, _lib.ptr(K_e),
+                                                    _lib.ptr(plan.slot_rank[0]), _lib.ptr(pat.nindptr), pat.max_deg,
+                                                    _lib.ptr(J_vals), 0, _lib.ptr(pat.nindices), _lib.ptr(mask))
     kernel_ms = {k: timed(f, args.steps, 1)[0] for k, f in kernels.items()}
     assemble_step_again = assembly_step()        # leave J_vals / R consistent for the solve below
     xv = torch.rand(F, dtype=torch.float64, device=dev)
@@ -345,12 +354,24 @@ def main():
         hbm, hbm_src = peaks()
         total_E = E * world
         value = total_E / (ms_step * 1e-3)
-        # algorithmic bytes per assembly pass: 8 nnz + slot map (2 B/entry here) + conn + coords + u + R
+        # algorithmic bytes (the slot map is 2 bytes per node pair here):
+        #   Jacobian assembly kernel  B_J = 8 nnz + 2 N^2 E + 4 N E + 8 D V
+        #   whole assembly pass       B_A = B_J + 8 F (u) + 8 F (R) + 16 F (mask, values) + 8 n_mp
         n_mp = {"M": 2, "EM": 2 * E, "EQM": 16 * E}[args.layout]
-        alg_bytes = 8 * nnz + 2 * 64 * E + 4 * 8 * E + 8 * 3 * V + 8 * F + 8 * F + 16 * F + 8 * n_mp
-        dom = max(("element_tangent", "assemble_csr"), key=lambda k: kernel_ms[k])
-        asm_ms = kernel_ms["element_tangent"] + kernel_ms["assemble_csr"]
-        achieved = alg_bytes / (asm_ms * 1e-3) / 1e9
+        bytes_J = 8 * nnz + 2 * 64 * E + 4 * 8 * E + 8 * 3 * V
+        alg_bytes = bytes_J + 8 * F + 8 * F + 16 * F + 8 * n_mp
+        if "assemble_fused_hex8" in kernel_ms:
+            dom, dom_ms = "feb200_assemble_fused_hex8 (k_fused_hex8_iso)", kernel_ms["assemble_fused_hex8"]
+        else:
+            dom = "element_tangent + assemble_csr (two-pass assembly)"
+            dom_ms = kernel_ms["element_tangent"] + kernel_ms["assemble_csr"]
+        achieved = bytes_J / (dom_ms * 1e-3) / 1e9
+        traffic = None
+        try:        # dram bytes of the dominant kernel from the committed ncu --set full capture of this configuration
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                traffic = json.load(f).get(f"fused_n{n}_{args.layout}") if "assemble_fused_hex8" in kernel_ms else None
+        except Exception:
+            pass
         spmv_bytes = 8 * nnz + 4 * (nnz // 9) + 8 * (V + 1) + 16 * F
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -360,10 +381,11 @@ def main():
                                    f"residual + Jacobian CSR assembly with fused Dirichlet elimination; material layout ({args.layout})",
                        "elements_per_gpu": E, "dofs_per_gpu": F, "nnz_per_gpu": nnz, "l2_policy": "inputs larger than L2",
                        "setup_s": t_setup},
-            "roofline": {"bound": "hbm", "kernel": f"element_tangent + assemble_csr (two-pass assembly; dominant: {dom})",
-                         "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
-                         "peak_source": hbm_src, "algorithmic_bytes": alg_bytes,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                         "frac": achieved / hbm, "traffic": traffic, "peak_source": hbm_src, "algorithmic_bytes": bytes_J,
                          "kernel_ms": kernel_ms,
+                         "assembly_pass": {"algorithmic_bytes": alg_bytes, "achieved": alg_bytes / (ms_step * 1e-3) / 1e9,
+                                           "frac": alg_bytes / (ms_step * 1e-3) / 1e9 / hbm},
                          "spmv": {"achieved": spmv_bytes / (kernel_ms["spmv"] * 1e-3) / 1e9, "peak": hbm,
                                   "frac": spmv_bytes / (kernel_ms["spmv"] * 1e-3) / 1e9 / hbm, "algorithmic_bytes": spmv_bytes}},
             "newton_cg": newton,
