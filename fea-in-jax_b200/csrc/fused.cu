@@ -28,7 +28,7 @@ constexpr int G_STRIDE = 26;             // doubles per (element, node) gradient
 constexpr int EL_STRIDE = 8 * G_STRIDE + 2;   // doubles per element in G: records of consecutive elements are 4 banks apart
 constexpr int XS_STRIDE = 25;            // doubles per element coordinate record (24 used)
 constexpr int DPHI_STRIDE = 25;          // doubles per quadrature point in the basis table (24 used)
-constexpr int WS_DOUBLES = 32 * 19 + 1;                // per-warp staging: block (k, b) at (4k + b/2)*19 + (b&1)*9 (odd lane stride)
+constexpr int WS_DOUBLES = FUSED_MAXVAL * 8 * 9;      // per-warp staging: block (k, b) at (k*8+b)*9
 constexpr int PF = 2;                    // element-node prefetch registers per thread: te_cap*8 <= PF*THREADS (te_cap <= 96)
 constexpr int PN = (FUSED_MAXDEG * 32 + FUSED_THREADS - 1) / FUSED_THREADS;   // neighbour-table entries per thread
 
@@ -103,12 +103,6 @@ k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const doub
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < FUSED_Q * 24; i += FUSED_THREADS) s_dphi[(i / 24) * DPHI_STRIDE + (i % 24)] = b.dphi[i];
-
-    static_assert(FUSED_THREADS % 8 == 0, "P1 keeps the basis table of quadrature point tid & 7 in registers");
-    double dphi_q[24];
-#pragma unroll
-    for (int i = 0; i < 24; ++i) dphi_q[i] = b.dphi[(tid & 7) * 24 + i];
-    const double W_q = b.W[tid & 7];
 
     TilePrefetch pf;
     auto level_a = [&](int tile) {
@@ -223,8 +217,8 @@ k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const doub
         for (int i = tid; i < TE * 8; i += FUSED_THREADS) {
             const int le = i >> 3, q = i & 7;
             double g[24];
-            const double dt = shape_gradients<8, 3>(xs + le * XS_STRIDE, dphi_q, g);
-            wdet[i] = dt * W_q;
+            const double dt = shape_gradients<8, 3>(xs + le * XS_STRIDE, s_dphi + q * DPHI_STRIDE, g);
+            wdet[i] = dt * b.W[q];
 #pragma unroll
             for (int n = 0; n < 8; ++n)
 #pragma unroll
@@ -277,7 +271,7 @@ k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const doub
                                 }
                         }
                         const double tr = mu * (S[0] + S[4] + S[8]);
-                        double* dst = ws + lane * 19 + bi * 9;
+                        double* dst = ws + (k * 8 + bn) * 9;
 #pragma unroll
                         for (int d = 0; d < 3; ++d)
 #pragma unroll
@@ -301,7 +295,7 @@ k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const doub
                     const unsigned int bsel = (unsigned int)(src & 0xffull);
                     src >>= 8;
                     if (bsel != 0xffu) {
-                        const double* sp = ws + (4 * k + (bsel >> 1)) * 19 + (bsel & 1u) * 9;
+                        const double* sp = ws + (k * 8 + bsel) * 9;
 #pragma unroll
                         for (int c = 0; c < 9; ++c) acc[c] += sp[c];
                     }
