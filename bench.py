@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the feb200 hot path (contract: see the task statement / DESIGN.md "Measurement").
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--n 200] [--impl feb200|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--grid 200] [--impl feb200|reference]
 
 N=1 workload (BASELINE.json configs[1]): 3-D hex8 linear elasticity on a uniform n^3 grid (n=200: 8 M
 elements, 24.4 M DoFs, 1.95e9 non-zeros), interior nodes jittered, batch-constant isotropic material.
@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--n", type=int, default=200, help="elements per axis of the hex8 grid (per rank)")
+    ap.add_argument("--grid", dest="n", type=int, default=200, help="elements per axis of the hex8 grid (per rank)")
     ap.add_argument("--impl", default="feb200", choices=["feb200", "reference"])
     ap.add_argument("--cg-iters", type=int, default=100)
     ap.add_argument("--cpu-n", type=int, default=20, help="grid size of the bounded CPU-baseline sample")
