@@ -284,7 +284,7 @@ def main():
     xv = torch.rand(F, dtype=torch.float64, device=dev)
     yv = torch.empty_like(xv)
     spmv = lambda: _lib.call("feb200_spmv", pat.V, pat.U, _lib.ptr(pat.nindptr), _lib.ptr(pat.nindices), _lib.ptr(J_vals),
-                             _lib.ptr(xv), _lib.ptr(yv), None, None, 0, pat.max_deg)
+                             _lib.ptr(xv), _lib.ptr(yv), None, None, 0)
     kernel_ms["spmv"] = timed(spmv, max(args.steps, 10), 3)[0]
 
     # ---- Newton-CG step: assembly + fixed number of CG iterations + update + residual re-evaluation

@@ -63,57 +63,7 @@ __device__ __forceinline__ double spmv_vertex(int64_t a, int lane, const int64_t
     return d;
 }
 
-// Variant for vertex degree <= 32: the row panel (U rows of U*deg contiguous doubles) is read as ONE flat, fully
-// coalesced stream (lane t, t+32, ...: full 32-byte sectors, streaming hint); the gathered x values of the <= 32
-// neighbours sit in a per-warp shared-memory strip indexed by the column inside the row.
 template <int U>
-__device__ __forceinline__ double spmv_vertex_flat(int64_t a, int lane, const int64_t* __restrict__ nindptr,
-                                                   const int32_t* __restrict__ nindices, const double* __restrict__ values,
-                                                   const double* __restrict__ x, double* __restrict__ y, double* sx) {
-    const int64_t p0 = nindptr[a];
-    const int deg = (int)(nindptr[a + 1] - p0);
-    const double* val = values + (int64_t)U * U * p0;
-    const int row_len = U * deg, total = U * row_len;
-    constexpr int MAXIT = (U * U * 32 + 31) / 32;          // U*U*deg / 32 rounded up for deg = 32
-    double v[MAXIT];
-#pragma unroll
-    for (int it = 0; it < MAXIT; ++it) {
-        const int t = lane + 32 * it;
-        v[it] = (t < total) ? __ldcs(val + t) : 0.0;
-    }
-    if (lane < deg) {
-        const int64_t bnode = nindices[p0 + lane];
-#pragma unroll
-        for (int j = 0; j < U; ++j) sx[U * lane + j] = x[bnode * U + j];
-    }
-    __syncwarp();
-    double acc[U];
-#pragma unroll
-    for (int i = 0; i < U; ++i) acc[i] = 0.0;
-#pragma unroll
-    for (int it = 0; it < MAXIT; ++it) {
-        const int t = lane + 32 * it;
-        if (t < total) {
-            const int i = t / row_len;
-            const double pr = v[it] * sx[t - i * row_len];
-#pragma unroll
-            for (int ii = 0; ii < U; ++ii) acc[ii] += (i == ii) ? pr : 0.0;
-        }
-    }
-    __syncwarp();
-    double d = 0.0;
-#pragma unroll
-    for (int i = 0; i < U; ++i) {
-        acc[i] = warp_sum(acc[i]);
-        if (lane == 0) {
-            y[a * U + i] = acc[i];
-            d += x[a * U + i] * acc[i];
-        }
-    }
-    return d;
-}
-
-template <int U, bool FLAT>
 __global__ void __launch_bounds__(256) k_spmv(int64_t V, const int64_t* __restrict__ nindptr,
                                               const int32_t* __restrict__ nindices, const double* __restrict__ values,
                                               const double* __restrict__ x, double* __restrict__ y, double* dot_out,
@@ -121,10 +71,8 @@ __global__ void __launch_bounds__(256) k_spmv(int64_t V, const int64_t* __restri
     if (counters && counters[C_DONE]) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     double d[1] = {0.0};
-    __shared__ double sx_all[8 * 32 * U];
     for (int64_t a = (int64_t)blockIdx.x * wpb + warp; a < V; a += (int64_t)gridDim.x * wpb)
-        d[0] += FLAT ? spmv_vertex_flat<U>(a, lane, nindptr, nindices, values, x, y, sx_all + warp * 32 * U)
-                     : spmv_vertex<U>(a, lane, nindptr, nindices, values, x, y);
+        d[0] += spmv_vertex<U>(a, lane, nindptr, nindices, values, x, y);
     if (!dot_out && !scalars) return;
     __shared__ double red[32];
     if (lane != 0) d[0] = 0.0;
@@ -264,24 +212,21 @@ static inline int reduce_grid(int64_t n, int block) {
 
 template <int U>
 static void launch_spmv(cudaStream_t st, int64_t V, const int64_t* nindptr, const int32_t* nindices, const double* values,
-                        const double* x, double* y, double* dot_out, ReduceWs ws, const int32_t* counters, double* scalars,
-                        bool flat) {
+                        const double* x, double* y, double* dot_out, ReduceWs ws, const int32_t* counters, double* scalars) {
     int64_t g = ceil_div(V, 8);
     int64_t cap = (int64_t)sm_count() * 8;
     if (dot_out || scalars) cap = MAX_PARTIALS < cap ? MAX_PARTIALS : cap;
     if (g > cap) g = cap;
     if (g < 1) g = 1;
-    if (flat) k_spmv<U, true><<<(int)g, 256, 0, st>>>(V, nindptr, nindices, values, x, y, dot_out, ws, counters, scalars);
-    else k_spmv<U, false><<<(int)g, 256, 0, st>>>(V, nindptr, nindices, values, x, y, dot_out, ws, counters, scalars);
+    k_spmv<U><<<(int)g, 256, 0, st>>>(V, nindptr, nindices, values, x, y, dot_out, ws, counters, scalars);
 }
 
 static int spmv_dispatch(cudaStream_t st, int64_t V, int U, const int64_t* nindptr, const int32_t* nindices,
                          const double* values, const double* x, double* y, double* dot_out, ReduceWs ws,
-                         const int32_t* counters, double* scalars, int max_deg = 0) {
-    const bool flat = max_deg > 0 && max_deg <= 32;
-    if (U == 3) launch_spmv<3>(st, V, nindptr, nindices, values, x, y, dot_out, ws, counters, scalars, flat);
-    else if (U == 2) launch_spmv<2>(st, V, nindptr, nindices, values, x, y, dot_out, ws, counters, scalars, flat);
-    else if (U == 1) launch_spmv<1>(st, V, nindptr, nindices, values, x, y, dot_out, ws, counters, scalars, flat);
+                         const int32_t* counters, double* scalars) {
+    if (U == 3) launch_spmv<3>(st, V, nindptr, nindices, values, x, y, dot_out, ws, counters, scalars);
+    else if (U == 2) launch_spmv<2>(st, V, nindptr, nindices, values, x, y, dot_out, ws, counters, scalars);
+    else if (U == 1) launch_spmv<1>(st, V, nindptr, nindices, values, x, y, dot_out, ws, counters, scalars);
     else FEB_REQUIRE(false, FEB200_ERR_UNSUPPORTED, "spmv: U=%d not supported", U);
     return FEB200_OK;
 }
@@ -305,13 +250,12 @@ extern "C" {
 size_t feb200_reduce_workspace_bytes(void) { return REDUCE_WS_BYTES; }
 
 int feb200_spmv(feb200_stream s, int64_t V, int32_t U, const int64_t* nindptr, const int32_t* nindices,
-                const double* values, const double* x, double* y, double* dot_out, void* ws, size_t ws_bytes,
-                int32_t max_deg) {
+                const double* values, const double* x, double* y, double* dot_out, void* ws, size_t ws_bytes) {
     FEB_REQUIRE(nindptr && nindices && values && x && y, FEB200_ERR_INVALID, "spmv: null pointer");
     FEB_REQUIRE(!dot_out || (ws && ws_bytes >= REDUCE_WS_BYTES), FEB200_ERR_WORKSPACE, "spmv: reduce workspace too small");
     if (V == 0) return FEB200_OK;
     ReduceWs r = ws ? reduce_ws(ws) : ReduceWs{nullptr, nullptr};
-    int rc = spmv_dispatch(as_stream(s), V, U, nindptr, nindices, values, x, y, dot_out, r, nullptr, nullptr, max_deg);
+    int rc = spmv_dispatch(as_stream(s), V, U, nindptr, nindices, values, x, y, dot_out, r, nullptr, nullptr);
     if (rc) return rc;
     FEB_CHECK_LAUNCH("spmv");
     return FEB200_OK;
@@ -350,7 +294,7 @@ static int cg_stage(cudaStream_t cs, const feb200_cg_state* st, int stage, doubl
             FEB_CUDA(cudaMemsetAsync(st->hist, 0, (size_t)st->maxiter * sizeof(double), cs));
             if (st->V > 0)
                 rc = spmv_dispatch(cs, st->V, st->U, st->nindptr, st->nindices, st->values, st->x, st->Ap, nullptr, r,
-                                   nullptr, nullptr, st->max_deg);
+                                   nullptr, nullptr);
             break;
         case FEB200_CG_INIT_VECTORS:
             k_cg_init_vectors<<<reduce_grid(n, 256), 256, 0, cs>>>(n, st->b, st->Ap, st->inv_diag, st->weights, st->r,
@@ -362,7 +306,7 @@ static int cg_stage(cudaStream_t cs, const feb200_cg_state* st, int stage, doubl
         case FEB200_CG_SPMV:     // Ap = A p (+ p.Ap when there are no ownership weights)
             if (st->V > 0)
                 rc = spmv_dispatch(cs, st->V, st->U, st->nindptr, st->nindices, st->values, st->p, st->Ap, nullptr, r,
-                                   st->counters, st->weights ? nullptr : st->scalars, st->max_deg);
+                                   st->counters, st->weights ? nullptr : st->scalars);
             break;
         case FEB200_CG_PAP:      // weighted p.Ap -> scalars[1] (local; caller all-reduces)
             k_dot<<<reduce_grid(n, 256), 256, 0, cs>>>(n, st->p, st->Ap, st->weights, st->scalars + S_PAP, r, st->counters);

@@ -44,7 +44,7 @@ class FusedPlan(Structure):
 
 
 class CGState(Structure):
-    _fields_ = [("V", c_int64), ("U", c_int32), ("maxiter", c_int32), ("max_deg", c_int32), ("reserved", c_int32),
+    _fields_ = [("V", c_int64), ("U", c_int32), ("maxiter", c_int32),
                 ("nindptr", c_void_p), ("nindices", c_void_p), ("values", c_void_p), ("inv_diag", c_void_p),
                 ("weights", c_void_p), ("b", c_void_p), ("x", c_void_p), ("r", c_void_p), ("p", c_void_p), ("Ap", c_void_p),
                 ("hist", c_void_p), ("scalars", c_void_p), ("counters", c_void_p), ("ws", c_void_p),
@@ -85,7 +85,7 @@ SIGNATURES = {
     "feb200_coo_segment_sum": (c_int32, [_P, _I64, _P, _P, _P, _P, _P, _I64, _P, _P, _P]),
     "feb200_coo_rows_to_indptr": (c_int32, [_P, _I64, _P, _I64, _P]),
     "feb200_reduce_workspace_bytes": (_SZ, []),
-    "feb200_spmv": (c_int32, [_P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _SZ, _I32]),
+    "feb200_spmv": (c_int32, [_P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _SZ]),
     "feb200_spmv_csr": (c_int32, [_P, _I64, _P, _P, _P, _P, _P]),
     "feb200_dot": (c_int32, [_P, _I64, _P, _P, _P, _P, _SZ]),
     "feb200_cg_init": (c_int32, [_P, POINTER(CGState), _F64, _F64]),

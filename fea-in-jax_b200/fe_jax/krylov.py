@@ -45,7 +45,7 @@ def cg_on_pattern(pat: NodePattern, values, b, x0, tol, atol, maxiter, inv_diag=
     scalars = torch.zeros(8, dtype=torch.float64, device=dev)
     counters = torch.zeros(4, dtype=torch.int32, device=dev)
     ws = _lib.workspace(lib.feb200_reduce_workspace_bytes(), dev)
-    st = _lib.CGState(V=pat.V, U=pat.U, maxiter=maxiter, max_deg=pat.max_deg, nindptr=_lib.ptr(pat.nindptr), nindices=_lib.ptr(pat.nindices),
+    st = _lib.CGState(V=pat.V, U=pat.U, maxiter=maxiter, nindptr=_lib.ptr(pat.nindptr), nindices=_lib.ptr(pat.nindices),
                       values=_lib.ptr(values), inv_diag=_lib.ptr(inv_diag), b=_lib.ptr(b), x=_lib.ptr(x), r=_lib.ptr(r),
                       p=_lib.ptr(p), Ap=_lib.ptr(Ap), hist=_lib.ptr(hist), scalars=_lib.ptr(scalars),
                       counters=_lib.ptr(counters), ws=_lib.ptr(ws), ws_bytes=ws.numel())

@@ -277,7 +277,7 @@ class DistributedProblem:
                     d = csr_diagonal(pat, vals)
                     keep.append(d)
                     inv_diag = d
-                st = _lib.CGState(V=pat.V, U=pat.U, maxiter=maxiter, max_deg=pat.max_deg, nindptr=_lib.ptr(pat.nindptr),
+                st = _lib.CGState(V=pat.V, U=pat.U, maxiter=maxiter, nindptr=_lib.ptr(pat.nindptr),
                                   nindices=_lib.ptr(pat.nindices), values=_lib.ptr(vals), inv_diag=None,
                                   weights=_lib.ptr(rp.weights), b=_lib.ptr(b), x=_lib.ptr(x), r=_lib.ptr(r), p=_lib.ptr(p),
                                   Ap=_lib.ptr(Ap), hist=_lib.ptr(hist), scalars=_lib.ptr(scalars),

@@ -104,7 +104,7 @@ def pattern_matvec(pat: NodePattern, vals, v):
     x = as_device(v, torch.float64)
     y = torch.empty_like(x)
     _lib.call("feb200_spmv", pat.V, pat.U, _lib.ptr(pat.nindptr), _lib.ptr(pat.nindices), _lib.ptr(vals), _lib.ptr(x),
-              _lib.ptr(y), None, None, 0, pat.max_deg)
+              _lib.ptr(y), None, None, 0)
     return y
 
 

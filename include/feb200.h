@@ -200,10 +200,8 @@ int feb200_coo_rows_to_indptr(feb200_stream s, int64_t nnz, const int64_t* row, 
 /* ------------------------------------------------------------------ Krylov (solve_cg.py:20-63)
  * y = A x on the node-pattern CSR.  If dot_out != NULL also dot_out[0] = x.y (deterministic). */
 size_t feb200_reduce_workspace_bytes(void);
-/* max_deg: largest vertex degree of the pattern (0 = unknown); <= 32 selects the flat, fully coalesced variant */
 int feb200_spmv(feb200_stream s, int64_t V, int32_t U, const int64_t* nindptr, const int32_t* nindices,
-                const double* values, const double* x, double* y, double* dot_out, void* ws, size_t ws_bytes,
-                int32_t max_deg);
+                const double* values, const double* x, double* y, double* dot_out, void* ws, size_t ws_bytes);
 /* generic CSR (int64 indptr / indices), one warp per row */
 int feb200_spmv_csr(feb200_stream s, int64_t n_rows, const int64_t* indptr, const int64_t* indices,
                     const double* values, const double* x, double* y);
@@ -220,8 +218,6 @@ typedef struct {
     int64_t V;
     int32_t U;
     int32_t maxiter;
-    int32_t max_deg;          /* largest vertex degree (0 = unknown) */
-    int32_t reserved;
     const int64_t* nindptr;
     const int32_t* nindices;
     const double* values;

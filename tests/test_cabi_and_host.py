@@ -38,7 +38,7 @@ def test_bad_arguments_are_reported_not_crashed(built):
     lib = built.load()
     rc = lib.feb200_gather(None, None, 4, 3, 2, None, None)       # null pointers -> status + message, no launch
     assert rc == -1 and b"gather" in lib.feb200_last_error()
-    rc = lib.feb200_spmv(None, 10, 3, None, None, None, None, None, None, None, 0, 0)
+    rc = lib.feb200_spmv(None, 10, 3, None, None, None, None, None, None, None, 0)
     assert rc == -1
 
 
