@@ -29,15 +29,11 @@ static inline ReduceWs reduce_ws(void* ws) {
     return r;
 }
 
-// y = A x for the vertices handled by this warp; returns sum_i x[U a + i] * y[U a + i] in lane 0.
-// Each of the U rows of the panel (U*deg contiguous doubles) is streamed with fully coalesced 8-byte loads
-// (lane t, t+32, ...), so every 32-byte sector passes through L1 once; the x values of the neighbours are
-// gathered once per vertex into a per-warp shared-memory strip sx[U*r + j] that has the same index as the
-// column inside the row.
+// y = A x for the vertices handled by this warp; returns sum_i x[U a + i] * y[U a + i] in lane 0
 template <int U>
 __device__ __forceinline__ double spmv_vertex(int64_t a, int lane, const int64_t* __restrict__ nindptr,
                                               const int32_t* __restrict__ nindices, const double* __restrict__ values,
-                                              const double* __restrict__ x, double* __restrict__ y, double* sx) {
+                                              const double* __restrict__ x, double* __restrict__ y) {
     const int64_t p0 = nindptr[a];
     const int deg = (int)(nindptr[a + 1] - p0);
     const double* val = values + (int64_t)U * U * p0;
@@ -45,29 +41,15 @@ __device__ __forceinline__ double spmv_vertex(int64_t a, int lane, const int64_t
     double acc[U];
 #pragma unroll
     for (int i = 0; i < U; ++i) acc[i] = 0.0;
-    for (int r0 = 0; r0 < deg; r0 += 32) {                    // 32 neighbours (U*32 columns) per pass
-        const int r = r0 + lane;
-        if (r < deg) {
-            const int64_t bnode = nindices[p0 + r];
+    for (int r = lane; r < deg; r += 32) {
+        const int64_t bnode = nindices[p0 + r];
+        double xb[U];
 #pragma unroll
-            for (int j = 0; j < U; ++j) sx[U * lane + j] = x[bnode * U + j];
-        }
-        __syncwarp();
-        const int c0 = U * r0;
-        const int ncol = (row_len - c0) < U * 32 ? (row_len - c0) : U * 32;
-        double xs[U];
+        for (int j = 0; j < U; ++j) xb[j] = x[bnode * U + j];
 #pragma unroll
-        for (int it = 0; it < U; ++it) xs[it] = (lane + 32 * it < ncol) ? sx[lane + 32 * it] : 0.0;
+        for (int i = 0; i < U; ++i)
 #pragma unroll
-        for (int i = 0; i < U; ++i) {
-            const double* row = val + (int64_t)i * row_len + c0;
-#pragma unroll
-            for (int it = 0; it < U; ++it) {
-                const int t = lane + 32 * it;
-                if (t < ncol) acc[i] += __ldcs(row + t) * xs[it];
-            }
-        }
-        __syncwarp();
+            for (int j = 0; j < U; ++j) acc[i] += val[i * row_len + U * r + j] * xb[j];
     }
     double d = 0.0;
 #pragma unroll
@@ -89,9 +71,8 @@ __global__ void __launch_bounds__(256) k_spmv(int64_t V, const int64_t* __restri
     if (counters && counters[C_DONE]) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     double d[1] = {0.0};
-    __shared__ double sx_all[8 * 32 * U];
     for (int64_t a = (int64_t)blockIdx.x * wpb + warp; a < V; a += (int64_t)gridDim.x * wpb)
-        d[0] += spmv_vertex<U>(a, lane, nindptr, nindices, values, x, y, sx_all + warp * 32 * U);
+        d[0] += spmv_vertex<U>(a, lane, nindptr, nindices, values, x, y);
     if (!dot_out && !scalars) return;
     __shared__ double red[32];
     if (lane != 0) d[0] = 0.0;
