@@ -22,7 +22,13 @@ namespace feb {
 constexpr int FUSED_Q = 8;
 constexpr int FUSED_MAXVAL = 8;          // incident slots per vertex handled (lane = 4*k + b/2)
 constexpr int FUSED_MAXDEG = 32;         // neighbour blocks per vertex (one lane each; hex8: 27)
-constexpr int FUSED_WARPS = 12;
+#ifndef FEB_FUSED_WARPS
+#define FEB_FUSED_WARPS 12
+#endif
+#ifndef FEB_FUSED_MINBLOCKS
+#define FEB_FUSED_MINBLOCKS 1
+#endif
+constexpr int FUSED_WARPS = FEB_FUSED_WARPS;
 constexpr int FUSED_THREADS = FUSED_WARPS * 32;
 constexpr int G_STRIDE = 26;             // doubles per (element, node) gradient record (24 used): 16-byte aligned
 constexpr int EL_STRIDE = 8 * G_STRIDE + 2;   // doubles per element in G: records of consecutive elements are 4 banks apart
@@ -82,7 +88,7 @@ struct TilePrefetch {
 //   A  lane = 4*k + b/2 computes the two blocks K_e[a, b], K_e[a, b+1] of incident slot k  -> warp-private staging
 //   B  lane = neighbour rank r adds its <= 8 contributions in ascending slot order, eliminates, stores
 template <bool ELIM>
-__global__ void __launch_bounds__(FUSED_THREADS, 1)
+__global__ void __launch_bounds__(FUSED_THREADS, FEB_FUSED_MINBLOCKS)
 k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const double* __restrict__ x_vd,
                  const uint16_t* __restrict__ slot_rank, const int32_t* __restrict__ nindices,
                  const uint8_t* __restrict__ vflags, double* __restrict__ values) {
@@ -356,7 +362,7 @@ int feb200_assemble_fused_hex8(feb200_stream s, const feb200_batch* bp, const fe
     cudaStream_t st = as_stream(s);
     (void)row_ind;
     (void)nindptr;
-    int grid = plan->n_tiles < sm_count() ? plan->n_tiles : sm_count();
+    int grid = plan->n_tiles < sm_count() * FEB_FUSED_MINBLOCKS ? plan->n_tiles : sm_count() * FEB_FUSED_MINBLOCKS;
     if (vertex_flags) {
         auto kern = k_fused_hex8_iso<true>;
         FEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));

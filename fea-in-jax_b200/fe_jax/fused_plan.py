@@ -54,7 +54,11 @@ class FusedPlan:
 
 def build_fused_plan(vertices, conn32, row_ind, col_ind, nindptr=None):
     """Largest tile size whose tiles fit in shared memory: 32 (4x4x2 Morton cells), else 16, else 8 vertices."""
+    import os
+    first = int(os.environ.get("FEB200_FUSED_TN", "32"))
     for tn_cap, shift in ((32, 5), (16, 4), (8, 3)):
+        if tn_cap > first:
+            continue
         plan = _build(vertices, conn32, row_ind, col_ind, tn_cap, shift, nindptr)
         if plan is not None:
             return plan
