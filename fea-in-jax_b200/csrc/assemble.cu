@@ -25,18 +25,21 @@ __device__ __forceinline__ void store_panel(int lane, int64_t a, int deg, int64_
     constexpr int U2 = U * U;
     const int row_len = U * deg;
     double* dst = values + (int64_t)U2 * p0;
-    for (int t = lane; t < U * row_len; t += 32) {
-        double v = acc[t];
-        if (accumulate) v += dst[t];
-        if (mask) {
-            const int i = t / row_len, c = t - i * row_len;
-            const int r = c / U, j = c - r * U;
-            const int64_t colv = nindices[p0 + r];
-            const bool rm = mask[a * U + i] != 0.0;
-            const bool cm = mask[colv * U + j] != 0.0;
-            if (rm || cm) v = (rm && colv == a && i == j) ? 1.0 : 0.0;
+#pragma unroll
+    for (int i = 0; i < U; ++i) {                       // row by row: no division by the run-time row length
+        const bool rm = mask ? (mask[a * U + i] != 0.0) : false;
+        for (int c = lane; c < row_len; c += 32) {
+            const int t = i * row_len + c;
+            double v = acc[t];
+            if (accumulate) v += dst[t];
+            if (mask) {
+                const int r = c / U, j = c - r * U;
+                const int64_t colv = nindices[p0 + r];
+                const bool cm = mask[colv * U + j] != 0.0;
+                if (rm || cm) v = (rm && colv == a && i == j) ? 1.0 : 0.0;
+            }
+            dst[t] = v;
         }
-        dst[t] = v;
     }
 }
 

@@ -85,9 +85,9 @@ __global__ void __launch_bounds__(BLOCK) k_residual_ct(feb200_batch b, const dou
             for (int i = 0; i < NU; ++i) s_out[threadIdx.x * (NU + 1) + i] = R[i];
         }
         __syncthreads();
-        const int64_t n_here = (b.E - e0 < BLOCK) ? (b.E - e0) : BLOCK;
-        for (int64_t i = threadIdx.x; i < n_here * NU; i += BLOCK) {
-            const int t = (int)(i / NU), c = (int)(i - (int64_t)t * NU);
+        const int n_here = (int)((b.E - e0 < BLOCK) ? (b.E - e0) : BLOCK);
+        for (int i = threadIdx.x; i < n_here * NU; i += BLOCK) {
+            const int t = i / NU, c = i - t * NU;                          // constant divisor, 32-bit
             R_e[e0 * NU + i] = s_out[t * (NU + 1) + c];
         }
         __syncthreads();
@@ -284,9 +284,10 @@ __global__ void __launch_bounds__(128) k_tangent_iso(feb200_batch b, int epb, in
                     for (int c = 0; c < D2; ++c) dst[bn * D2 + c] = acc[pass * NB + bn][c];
             }
             __syncthreads();
-            for (int64_t i = threadIdx.x; i < n_slots * PIECE; i += blockDim.x) {
-                const int64_t t = i / PIECE;
-                const int c = (int)(i - t * PIECE);
+            const int n_items = (int)n_slots * PIECE;
+            for (int i = threadIdx.x; i < n_items; i += blockDim.x) {
+                const int t = i / PIECE;                                   // constant divisor, 32-bit
+                const int c = i - t * PIECE;
                 K_e[(slot0 + t) * (int64_t)(N * D2) + pass * PIECE + c] = s_el[t * PSTRIDE + c];
             }
         }
