@@ -131,7 +131,7 @@ __device__ __forceinline__ void stage_geometry(const feb200_batch& b, int N, int
     double* xe = s_el + (size_t)e_l * per_el;
     double* ue = xe + NU;
     double* g = ue + NU;
-    double* wdet = g + (size_t)Q * NU;
+    double* wdet = g + (size_t)Q * (NU + 1);
     double* aux = wdet + Q;
     if (active) {
         const int64_t v = b.conn[e * N + a];
@@ -146,8 +146,8 @@ __device__ __forceinline__ void stage_geometry(const feb200_batch& b, int N, int
         int qs;
         const double* mp = mp_of(b, e, qs);
         for (int q = a; q < Q; q += N) {
-            double* gq = g + (size_t)q * NU;
-            const double dt = shape_gradients_rt<D>(N, xe, s_dphi + (size_t)q * NU, gq);
+            double* gq = g + (size_t)q * (NU + 1);
+            const double dt = shape_gradients_rt<D>(N, xe, s_dphi + (size_t)q * (NU + 1), gq);
             wdet[q] = dt * b.W[q];
             const double* mpq = mp + (int64_t)q * qs;
             if (iso_fast) {
@@ -191,8 +191,8 @@ __global__ void __launch_bounds__(128) k_tangent_iso(feb200_batch b, int epb, in
     static_assert(N % PASSES == 0, "PASSES must divide N");
     extern __shared__ double smem[];
     double* s_dphi = smem;
-    double* s_el = smem + (size_t)b.Q * NU;         // geometry staging, later reused as store staging
-    for (int i = threadIdx.x; i < b.Q * NU; i += blockDim.x) s_dphi[i] = b.dphi[i];
+    double* s_el = smem + (size_t)b.Q * (NU + 1);         // geometry staging, later reused as store staging
+    for (int i = threadIdx.x; i < b.Q * NU; i += blockDim.x) s_dphi[(i / NU) * (NU + 1) + i % NU] = b.dphi[i];   // padded rows
     const int e_l = threadIdx.x / N, a = threadIdx.x - e_l * N;
     const int Q = b.Q;
     const int n_slots_blk = epb * N;                // (element, node) slots handled per tile
@@ -208,10 +208,10 @@ __global__ void __launch_bounds__(128) k_tangent_iso(feb200_batch b, int epb, in
             for (int c = 0; c < D2; ++c) acc[bn][c] = 0.0;
         if (active) {
             const double* g = s_el + (size_t)e_l * per_el + 2 * NU;
-            const double* wdet = g + (size_t)Q * NU;
+            const double* wdet = g + (size_t)Q * (NU + 1);
             const double* aux = wdet + Q;
             for (int q = 0; q < Q; ++q) {
-                const double* gq = g + (size_t)q * NU;
+                const double* gq = g + (size_t)q * (NU + 1);
                 const double w = wdet[q];
                 double ga[D];
 #pragma unroll
@@ -303,8 +303,8 @@ __global__ void k_tangent_general_ct(feb200_batch b, int epb, int per_el, const 
     constexpr int NU = N * D, D2 = D * D, D4 = D2 * D2;
     extern __shared__ double smem[];
     double* s_dphi = smem;
-    double* s_el = smem + (size_t)b.Q * NU;
-    for (int i = threadIdx.x; i < b.Q * NU; i += blockDim.x) s_dphi[i] = b.dphi[i];
+    double* s_el = smem + (size_t)b.Q * (NU + 1);
+    for (int i = threadIdx.x; i < b.Q * NU; i += blockDim.x) s_dphi[(i / NU) * (NU + 1) + i % NU] = b.dphi[i];   // padded rows
     const int e_l = threadIdx.x / N, a = threadIdx.x - e_l * N;
     const int Q = b.Q;
     for (int64_t e0 = (int64_t)blockIdx.x * epb; e0 < b.E; e0 += (int64_t)gridDim.x * epb) {
@@ -314,7 +314,7 @@ __global__ void k_tangent_general_ct(feb200_batch b, int epb, int per_el, const 
         stage_geometry<D>(b, N, e_l, a, e, active, x_vd, u, mask, values, s_dphi, s_el, per_el, D4, false);
         if (!active) continue;
         const double* g = s_el + (size_t)e_l * per_el + 2 * NU;
-        const double* wdet = g + (size_t)Q * NU;
+        const double* wdet = g + (size_t)Q * (NU + 1);
         const double* aux = wdet + Q;
         double acc[N][D2];
 #pragma unroll
@@ -323,7 +323,7 @@ __global__ void k_tangent_general_ct(feb200_batch b, int epb, int per_el, const 
             for (int c = 0; c < D2; ++c) acc[bn][c] = 0.0;
         for (int q = 0; q < Q; ++q) {
             const double* A = aux + (size_t)q * D4;
-            const double* gq = g + (size_t)q * NU;
+            const double* gq = g + (size_t)q * (NU + 1);
             double t[D2][D];   // t[d*D+k][l] = w * sum_i g_a[i] A[i,d,k,l]
             const double w = wdet[q];
 #pragma unroll
@@ -363,8 +363,8 @@ __global__ void k_tangent_general_rt(feb200_batch b, int epb, int per_el, const 
     const int N = b.N, NU = N * D, Q = b.Q;
     extern __shared__ double smem[];
     double* s_dphi = smem;
-    double* s_el = smem + (size_t)Q * NU;
-    for (int i = threadIdx.x; i < Q * NU; i += blockDim.x) s_dphi[i] = b.dphi[i];
+    double* s_el = smem + (size_t)Q * (NU + 1);
+    for (int i = threadIdx.x; i < Q * NU; i += blockDim.x) s_dphi[(i / NU) * (NU + 1) + i % NU] = b.dphi[i];   // padded rows
     const int e_l = threadIdx.x / N, a = threadIdx.x - e_l * N;
     for (int64_t e0 = (int64_t)blockIdx.x * epb; e0 < b.E; e0 += (int64_t)gridDim.x * epb) {
         const int64_t e = e0 + e_l;
@@ -373,7 +373,7 @@ __global__ void k_tangent_general_rt(feb200_batch b, int epb, int per_el, const 
         stage_geometry<D>(b, N, e_l, a, e, active, x_vd, u, mask, values, s_dphi, s_el, per_el, D4, false);
         if (!active) continue;
         const double* g = s_el + (size_t)e_l * per_el + 2 * NU;
-        const double* wdet = g + (size_t)Q * NU;
+        const double* wdet = g + (size_t)Q * (NU + 1);
         const double* aux = wdet + Q;
         double* out = K_e + ((e * N + a) * (int64_t)N) * D2;
         for (int bn = 0; bn < N; ++bn) {
@@ -382,7 +382,7 @@ __global__ void k_tangent_general_rt(feb200_batch b, int epb, int per_el, const 
             for (int c = 0; c < D2; ++c) acc[c] = 0.0;
             for (int q = 0; q < Q; ++q) {
                 const double* A = aux + (size_t)q * D4;
-                const double* gq = g + (size_t)q * NU;
+                const double* gq = g + (size_t)q * (NU + 1);
                 const double w = wdet[q];
 #pragma unroll
                 for (int dk = 0; dk < D2; ++dk) {
@@ -440,10 +440,10 @@ static int launch_residual_ct(cudaStream_t st, const feb200_batch& b, const doub
 struct TangentCfg { int epb, per_el, threads; size_t smem; };
 static int tangent_cfg(const feb200_batch& b, int aux, TangentCfg& c, int max_threads = 256, int stage_doubles_per_thread = 0) {
     const int NU = b.N * b.D;
-    c.per_el = 2 * NU + b.Q * NU + b.Q + b.Q * aux;
+    c.per_el = 2 * NU + b.Q * (NU + 1) + b.Q + b.Q * aux;
     if (c.per_el < stage_doubles_per_thread * b.N) c.per_el = stage_doubles_per_thread * b.N;   // store staging aliases it
     while (c.per_el % 16 != 4) ++c.per_el;   // elements of one warp hit distinct shared-memory banks on broadcast reads
-    const size_t table = (size_t)b.Q * NU * sizeof(double);
+    const size_t table = (size_t)b.Q * (NU + 1) * sizeof(double);
     const size_t budget = 96 * 1024;
     int epb = max_threads / b.N;
     while (epb > 1 && table + (size_t)epb * c.per_el * sizeof(double) > budget) --epb;
