@@ -28,3 +28,4 @@ from .solver import (PreconditionerType, LinearSolverType, SolverOptions, Solver
                      Residual, Jacobian, JacobianDiagonl, linear_solve)
 from .newton import solve_nonlinear_step, solve_bvp
 from . import partition
+from .vtk_io import read_vtk, write_vtk

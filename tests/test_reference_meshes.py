@@ -1,0 +1,104 @@
+"""The reference's own unstructured test meshes (tests/meshes/*.vtk of the reference, converted to
+tests/golden/reference_meshes.npz by tests/golden/make_meshes.py) through the legacy-VTK reader and the
+CUDA path: the scatter-mean / gather identity of tests/test_maps.py, the Dirichlet check of
+tests/test_fea_solve.py:90 and assembly parity on the quadratic-triangle RVE mesh of tests/test_microscale_bvp.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import build_pair, material_params, rel_err
+from oracle import fe_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+os.environ.setdefault("FEB200_QUIET", "1")
+
+
+@pytest.fixture(scope="module")
+def meshes():
+    return np.load(os.path.join(ROOT, "tests", "golden", "reference_meshes.npz"))
+
+
+def test_vtk_roundtrip_and_fixture(tmp_path, meshes):
+    import __graft_entry__  # noqa: F401  (puts the package on sys.path)
+    from fe_jax.vtk_io import read_vtk, write_vtk
+    pts = meshes["polygon_mesh_0p5__points"]
+    blocks = [("line", meshes["polygon_mesh_0p5__line"]), ("triangle", meshes["polygon_mesh_0p5__triangle"]),
+              ("vertex", meshes["polygon_mesh_0p5__vertex"])]
+    for binary in (True, False):
+        f = tmp_path / f"m{int(binary)}.vtk"
+        write_vtk(str(f), pts, blocks, binary=binary)
+        p2, b2 = read_vtk(str(f))
+        assert np.array_equal(p2, pts)
+        assert [n for n, _ in b2] == ["line", "triangle", "vertex"]
+        assert all(np.array_equal(x[1], y[1]) for x, y in zip(blocks, b2))
+    src = "/root/reference/tests/meshes/polygon_mesh_0.5.vtk"
+    if os.path.exists(src):                      # build container only
+        p3, b3 = read_vtk(src)
+        assert np.array_equal(p3, pts) and np.array_equal(dict(b3)["triangle"], meshes["polygon_mesh_0p5__triangle"])
+
+
+@pytest.fixture(scope="module")
+def fj():
+    import __graft_entry__ as graft
+    graft.build()
+    assert torch.cuda.is_available()
+    import fe_jax
+    return fe_jax
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["polygon_mesh_0p5", "polygon_mesh_0p1", "polygon_mesh_0p05", "rectangle_with_hole"])
+def test_maps_on_reference_meshes(fj, meshes, name):
+    # tests/test_maps.py:27-34 of the reference
+    points = meshes[name + "__points"]
+    cells = meshes[name + "__triangle"].astype(np.uint64)
+    A = fj.mesh_to_sparse_assembly_map(points.shape[0], cells)
+    ri = orc.build_row_ind(points.shape[0], cells)
+    ci, _ = orc.build_col_ind_and_data(ri, cells)
+    assert np.array_equal(A.indptr.view(torch.int64).cpu().numpy()[0].astype(np.uint64), ri)
+    assert np.array_equal(A.indices.view(torch.int64).cpu().numpy()[0].astype(np.uint64), ci)
+    x_n = fj.mesh_to_jax(points, cells)
+    back = fj.transform_element_node_to_global_nosum(A, x_n).cpu().numpy()
+    used = np.unique(cells.astype(np.int64))
+    assert np.allclose(back[used], points[used, :2], atol=1e-14)
+
+
+@pytest.mark.gpu
+def test_bvp_on_reference_polygon_mesh(fj, meshes):
+    # problem of tests/test_fea_solve.py: random Dirichlet values on the boundary, per-point random modulus
+    points = meshes["polygon_mesh_0p1__points"][:, :2]
+    cells = meshes["polygon_mesh_0p1__triangle"]
+    boundary = np.unique(meshes["polygon_mesh_0p1__line"])
+    rng = np.random.default_rng(0)
+    bcs = np.stack([np.repeat(boundary, 2), np.tile([0, 1], boundary.shape[0])], axis=1)
+    vals = 0.001 * rng.random(bcs.shape[0])
+    mp = material_params("elastic_isotropic", 2, (cells.shape[0], 6), seed=1)
+    ebc, maps, token, prob, fb = build_pair(fj, points, [dict(cell="triangle", degree=1, qdeg=3, cells=cells,
+                                                             model="elastic_isotropic", mp=mp)])
+    opts = fj.SolverOptions(linear_precond_type=fj.PreconditionerType.JACOBI, linear_max_iter=3000)
+    u, res, _ = fj.solve_bvp(points, fb, fj.linear_elasticity_residual, None, bcs, vals, solver_options=opts)
+    dofs = 2 * bcs[:, 0] + bcs[:, 1]
+    assert np.array_equal(u.cpu().numpy()[dofs], vals)                       # tests/test_fea_solve.py:90
+    u_o, _, _ = orc.solve_bvp(points, prob.batches, None, bcs, vals, options={"precond": "JACOBI", "linear_max_iter": 3000})
+    assert rel_err(u, u_o) <= 1e-8
+
+
+@pytest.mark.gpu
+def test_assembly_on_reference_rve_mesh_tri6(fj, meshes):
+    # microscale_2D_r0.vtk: 11158 quadratic triangles (gmsh node order -> basix order), orthotropic material
+    points = meshes["microscale_2D_r0__points"][:, :2]
+    cells = meshes["microscale_2D_r0__triangle6"][:, [0, 1, 2, 4, 5, 3]]
+    mp = material_params("elastic_orthotropic", 2, (cells.shape[0],), seed=2)
+    ebc, maps, token, prob, _ = build_pair(fj, points, [dict(cell="triangle", degree=2, qdeg=4, cells=cells,
+                                                            model="elastic_orthotropic", mp=mp)])
+    u = 1e-4 * np.random.default_rng(3).normal(size=points.size)
+    R, _ = fj.calculate_residual_wo_dirichlet(token, ebc, maps, u)
+    assert rel_err(R, prob.residual_wo_dirichlet(u)) <= 1e-11
+    nnz = fj._calculate_jacobian_unique_nnz(prob.V, ebc)
+    assert nnz == prob.jacobian_unique_nnz()
+    J = fj.calculate_jacobian_wo_dirichlet(token, ebc, maps, u, nnz)
+    d_o, r_o, c_o = prob.jacobian_wo_dirichlet(u)
+    assert np.array_equal(J.row.cpu().numpy(), r_o) and np.array_equal(J.col.cpu().numpy(), c_o)
+    assert rel_err(J.data, d_o) <= 1e-11
