@@ -141,9 +141,26 @@ class TorchDistComm:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
 
 
+_HALO_CACHE = {}
+
+
+def _halo_meta(rank, nb):
+    """(touched vertex ids, True if some vertex is shared with more than one neighbour), cached per index set"""
+    key = (rank, tuple((p, idx.data_ptr(), int(idx.shape[0])) for p, idx in sorted(nb.items())))
+    hit = _HALO_CACHE.get(key)
+    if hit is None:
+        allidx = torch.cat([idx for idx in nb.values()])
+        touched = allidx.unique()
+        hit = (touched, bool(touched.shape[0] != allidx.shape[0]))
+        _HALO_CACHE[key] = hit
+    return hit
+
+
 def halo_sum(comm, meshes_idx, vectors, U):
     """In place: every interface DoF becomes the sum of the partial values of all ranks sharing it, added in
-    ascending rank order (identical bits on every sharer).  meshes_idx[i] = (rank, {p: local vertex ids (tensor)})."""
+    ascending rank order (identical bits on every sharer).  meshes_idx[i] = (rank, {p: local vertex ids (tensor)}).
+    When every interface vertex has exactly two sharers (slab partitions) the sum is own + received, which is
+    already order independent, so the received values are simply added."""
     send = []
     for (rank, nb), v in zip(meshes_idx, vectors):
         v3 = v.view(-1, U)
@@ -153,7 +170,11 @@ def halo_sum(comm, meshes_idx, vectors, U):
         if not nb:
             continue
         v3 = v.view(-1, U)
-        touched = torch.cat([idx for idx in nb.values()]).unique()
+        touched, multi = _halo_meta(rank, nb)
+        if not multi:
+            for p in sorted(nb):
+                v3.index_add_(0, nb[p], rcv[p])
+            continue
         own = v3[touched].clone()
         v3[touched] = 0.0
         placed = False
