@@ -34,7 +34,9 @@ constexpr int G_STRIDE = 26;             // doubles per (element, node) gradient
 constexpr int EL_STRIDE = 8 * G_STRIDE + 2;   // doubles per element in G: records of consecutive elements are 4 banks apart
 constexpr int XS_STRIDE = 25;            // doubles per element coordinate record (24 used)
 constexpr int DPHI_STRIDE = 25;          // doubles per quadrature point in the basis table (24 used)
-constexpr int WS_DOUBLES = FUSED_MAXVAL * 8 * 9;      // per-warp staging: block (k, b) at (k*8+b)*9
+constexpr int WS_DOUBLES = FUSED_MAXVAL * 8 * 9 + 4;  // per-warp staging: block (k, b) at (k*8+b)*9 + (k>>1): the per-k pad makes
+                                                      // both the writes (lane = 4k + b/2) and the reads (8 b's of one k) conflict-free
+constexpr int WD_STRIDE = 9;             // doubles per element in wdet (8 used, odd)
 constexpr int PF = 2;                    // element-node prefetch registers per thread: te_cap*8 <= PF*THREADS (te_cap <= 96)
 constexpr int PN = (FUSED_MAXDEG * 32 + FUSED_THREADS - 1) / FUSED_THREADS;   // neighbour-table entries per thread
 
@@ -47,7 +49,7 @@ static inline FusedSmem fused_layout(int tn_cap, int te_cap) {
     L.tn_cap = tn_cap;
     L.te_cap = te_cap;
     L.off_g = 0;
-    size_t g_doubles = (size_t)te_cap * EL_STRIDE + (size_t)te_cap * FUSED_Q;      // G + wdet
+    size_t g_doubles = (size_t)te_cap * EL_STRIDE + (size_t)te_cap * WD_STRIDE;    // G + wdet
     g_doubles = (g_doubles + 1) & ~(size_t)1;
     L.off_ws = g_doubles * 8;
     size_t ws_doubles = (size_t)FUSED_WARPS * WS_DOUBLES;                          // xs (te*25) aliases the start
@@ -87,7 +89,9 @@ struct TilePrefetch {
 // P0/P1 are CTA-wide (one barrier each); after that every warp works alone on one vertex at a time:
 //   A  lane = 4*k + b/2 computes the two blocks K_e[a, b], K_e[a, b+1] of incident slot k  -> warp-private staging
 //   B  lane = neighbour rank r adds its <= 8 contributions in ascending slot order, eliminates, stores
-template <bool ELIM>
+// UNIFORM (material layout (M,): one lambda, mu for the batch): the blocks S_ab are summed first and
+// K = lam S + mu S^T + mu tr(S) I is applied once per CSR block instead of once per contribution.
+template <bool ELIM, bool UNIFORM>
 __global__ void __launch_bounds__(FUSED_THREADS, FEB_FUSED_MINBLOCKS)
 k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const double* __restrict__ x_vd,
                  const uint16_t* __restrict__ slot_rank, const int32_t* __restrict__ nindices,
@@ -224,7 +228,7 @@ k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const doub
             const int le = i >> 3, q = i & 7;
             double g[24];
             const double dt = shape_gradients<8, 3>(xs + le * XS_STRIDE, s_dphi + q * DPHI_STRIDE, g);
-            wdet[i] = dt * b.W[q];
+            wdet[le * WD_STRIDE + q] = dt * b.W[q];
 #pragma unroll
             for (int n = 0; n < 8; ++n)
 #pragma unroll
@@ -250,7 +254,7 @@ k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const doub
                         double tmp[24];
 #pragma unroll
                         for (int j = 0; j < 12; ++j) { const double2 v = rec[j]; tmp[2 * j] = v.x; tmp[2 * j + 1] = v.y; }
-                        const double* w = wdet + le * 8;
+                        const double* w = wdet + le * WD_STRIDE;
 #pragma unroll
                         for (int q = 0; q < 8; ++q)
 #pragma unroll
@@ -276,13 +280,18 @@ k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const doub
                                     S[i * 3 + l] += wga[2 * j + 1][i] * gb1[l];
                                 }
                         }
-                        const double tr = mu * (S[0] + S[4] + S[8]);
-                        double* dst = ws + (k * 8 + bn) * 9;
+                        double* dst = ws + (k * 8 + bn) * 9 + (k >> 1);
+                        if (UNIFORM) {
 #pragma unroll
-                        for (int d = 0; d < 3; ++d)
+                            for (int c = 0; c < 9; ++c) dst[c] = S[c];
+                        } else {
+                            const double tr = mu * (S[0] + S[4] + S[8]);
 #pragma unroll
-                            for (int kk = 0; kk < 3; ++kk)
-                                dst[d * 3 + kk] = lam * S[d * 3 + kk] + mu * S[kk * 3 + d] + (d == kk ? tr : 0.0);
+                            for (int d = 0; d < 3; ++d)
+#pragma unroll
+                                for (int kk = 0; kk < 3; ++kk)
+                                    dst[d * 3 + kk] = lam * S[d * 3 + kk] + mu * S[kk * 3 + d] + (d == kk ? tr : 0.0);
+                        }
                     }
                 }
             }
@@ -301,10 +310,22 @@ k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const doub
                     const unsigned int bsel = (unsigned int)(src & 0xffull);
                     src >>= 8;
                     if (bsel != 0xffu) {
-                        const double* sp = ws + (k * 8 + bsel) * 9;
+                        const double* sp = ws + (k * 8 + bsel) * 9 + (k >> 1);
 #pragma unroll
                         for (int c = 0; c < 9; ++c) acc[c] += sp[c];
                     }
+                }
+                if (UNIFORM) {
+                    const double lam = lm[0], mu = lm[1];
+                    double S[9];
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) S[c] = acc[c];
+                    const double tr = mu * (S[0] + S[4] + S[8]);
+#pragma unroll
+                    for (int d = 0; d < 3; ++d)
+#pragma unroll
+                        for (int kk = 0; kk < 3; ++kk)
+                            acc[d * 3 + kk] = lam * S[d * 3 + kk] + mu * S[kk * 3 + d] + (d == kk ? tr : 0.0);
                 }
                 if (ELIM) {
                     const int32_t colv = nbr_s[a * FUSED_MAXDEG + r];
@@ -363,15 +384,19 @@ int feb200_assemble_fused_hex8(feb200_stream s, const feb200_batch* bp, const fe
     (void)row_ind;
     (void)nindptr;
     int grid = plan->n_tiles < sm_count() * FEB_FUSED_MINBLOCKS ? plan->n_tiles : sm_count() * FEB_FUSED_MINBLOCKS;
-    if (vertex_flags) {
-        auto kern = k_fused_hex8_iso<true>;
-        FEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-        kern<<<grid, FUSED_THREADS, L.total, st>>>(b, *plan, L, x_vd, slot_rank, nindices, vertex_flags, values);
-    } else {
-        auto kern = k_fused_hex8_iso<false>;
-        FEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-        kern<<<grid, FUSED_THREADS, L.total, st>>>(b, *plan, L, x_vd, slot_rank, nindices, vertex_flags, values);
+    const bool uniform = (b.layout == FEB200_LAYOUT_M);
+#define FEB_FUSED_LAUNCH(EL, UN)                                                                                       \
+    {                                                                                                                  \
+        auto kern = k_fused_hex8_iso<EL, UN>;                                                                          \
+        FEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));               \
+        kern<<<grid, FUSED_THREADS, L.total, st>>>(b, *plan, L, x_vd, slot_rank, nindices, vertex_flags, values);      \
     }
+    if (vertex_flags) {
+        if (uniform) FEB_FUSED_LAUNCH(true, true) else FEB_FUSED_LAUNCH(true, false)
+    } else {
+        if (uniform) FEB_FUSED_LAUNCH(false, true) else FEB_FUSED_LAUNCH(false, false)
+    }
+#undef FEB_FUSED_LAUNCH
     FEB_CHECK_LAUNCH("assemble_fused_hex8");
     return FEB200_OK;
 }

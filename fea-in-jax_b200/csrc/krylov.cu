@@ -49,7 +49,7 @@ __device__ __forceinline__ double spmv_vertex(int64_t a, int lane, const int64_t
 #pragma unroll
         for (int i = 0; i < U; ++i)
 #pragma unroll
-            for (int j = 0; j < U; ++j) acc[i] += val[i * row_len + U * r + j] * xb[j];
+            for (int j = 0; j < U; ++j) acc[i] += __ldcs(val + i * row_len + U * r + j) * xb[j];
     }
     double d = 0.0;
 #pragma unroll
