@@ -24,8 +24,11 @@ __device__ __forceinline__ double load_u(const double* __restrict__ u, const dou
 // residual, compile-time N: registers for x, u, R; dphi / W staged in shared memory; the element-major
 // result is transposed through shared memory so that the global stores are coalesced.
 // ------------------------------------------------------------------------------------------------
+#ifndef FEB_RES_MINBLOCKS
+#define FEB_RES_MINBLOCKS 1
+#endif
 template <int N, int D, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_residual_ct(feb200_batch b, const double* __restrict__ x_vd,
+__global__ void __launch_bounds__(BLOCK, FEB_RES_MINBLOCKS) k_residual_ct(feb200_batch b, const double* __restrict__ x_vd,
                                                        const double* __restrict__ u, const double* __restrict__ mask,
                                                        const double* __restrict__ values, double* __restrict__ R_e) {
     constexpr int NU = N * D;
