@@ -172,11 +172,33 @@ def run_reference(args):
                                        f"{cores} host cores (one process per core, aggregate throughput); "
                                        "the reference's own JAX-CPU path cannot run (no jax in the image)"},
             "e2e": {"value": eps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _protect_stdout():
+    """Native libraries (NCCL prints its version banner) must not pollute the single JSON line on stdout:
+    route fd 1 to stderr for the whole run and keep the real stdout for emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
     args = parse()
+    _protect_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
@@ -418,7 +440,7 @@ def main():
             line["cpu_baseline"] = {"value": eps, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"oracle reference-style assembly on a {args.cpu_n}^3 hex8 grid ({Ec} elements, "
                                               f"{sec:.1f} s) on {cores} host cores concurrently (aggregate)"}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
