@@ -29,3 +29,4 @@ from .solver import (PreconditionerType, LinearSolverType, SolverOptions, Solver
 from .newton import solve_nonlinear_step, solve_bvp
 from . import partition
 from .vtk_io import read_vtk, write_vtk
+from .batched import solve_bvp_batched

@@ -102,3 +102,31 @@ def test_assembly_on_reference_rve_mesh_tri6(fj, meshes):
     d_o, r_o, c_o = prob.jacobian_wo_dirichlet(u)
     assert np.array_equal(J.row.cpu().numpy(), r_o) and np.array_equal(J.col.cpu().numpy(), c_o)
     assert rel_err(J.data, d_o) <= 1e-11
+
+
+@pytest.mark.gpu
+def test_batched_rve_solves_match_individual_solves(fj):
+    """Config 5 (vmap of many small BVPs): 12 copies of a quad4 RVE with per-copy modulus fields and boundary
+    values, solved as one block-diagonal problem, against the same problems solved one by one."""
+    V3, cells = fj.uniform_quad_grid(9, 9, np.array([[0.0, 1.0], [0.0, 1.0]]))
+    pts = V3[:, :2]
+    C, E = 12, cells.shape[0]
+    rng = np.random.default_rng(3)
+    mp = np.empty((C, E, 4, 2))
+    mp[..., 0] = 10e9 + 90e9 * rng.uniform(size=(C, E, 4))
+    mp[..., 1] = 0.25
+    edge = np.nonzero((pts[:, 0] < 1e-12) | (pts[:, 0] > 1 - 1e-12))[0]
+    bcs = np.stack([np.repeat(edge, 2), np.tile([0, 1], edge.shape[0])], axis=1)
+    vals = 1e-3 * rng.uniform(size=(C, bcs.shape[0]))
+    fe = fj.FiniteElementType(fj.CellType.quadrilateral, fj.ElementFamily.P, 1, fj.LagrangeVariant.equispaced,
+                              fj.QuadratureType.default, 2)
+    batch = fj.ElementBatch(fe_type=fe, n_dofs_per_basis=2, connectivity_en=cells, constitutive_model=fj.elastic_isotropic,
+                            material_params=mp[0])
+    opts = fj.SolverOptions(linear_precond_type=fj.PreconditionerType.JACOBI, linear_max_iter=4000)
+    u_b, res_b = fj.solve_bvp_batched(pts, [batch], fj.linear_elasticity_residual, bcs, vals, [mp], solver_options=opts)
+    assert u_b.shape == (C, pts.size)
+    for c in (0, 5, 11):
+        one = fj.ElementBatch(fe_type=fe, n_dofs_per_basis=2, connectivity_en=cells, constitutive_model=fj.elastic_isotropic,
+                              material_params=mp[c])
+        u1, _, _ = fj.solve_bvp(pts, [one], fj.linear_elasticity_residual, None, bcs, vals[c], solver_options=opts)
+        assert rel_err(u_b[c], u1.cpu().numpy()) <= 1e-7
