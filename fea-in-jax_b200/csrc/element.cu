@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(64) k_residual_rt(feb200_batch b, const double
 //   xe[N*D], ue[N*D], g[Q][N*D], wdet[Q], aux[Q][AUX]   (AUX = D^4 general, 2 isotropic fast path)
 // Thread t of the block is (element e_l = t / N, node a = t % N).
 // ------------------------------------------------------------------------------------------------
-template <int D>
+template <int D, int NCT = 0>
 __device__ __forceinline__ void stage_geometry(const feb200_batch& b, int N, int e_l, int a, int64_t e, bool active,
                                                const double* __restrict__ x_vd, const double* __restrict__ u,
                                                const double* __restrict__ mask, const double* __restrict__ values,
@@ -150,7 +150,18 @@ __device__ __forceinline__ void stage_geometry(const feb200_batch& b, int N, int
         const double* mp = mp_of(b, e, qs);
         for (int q = a; q < Q; q += N) {
             double* gq = g + (size_t)q * (NU + 1);
-            const double dt = shape_gradients_rt<D>(N, xe, s_dphi + (size_t)q * (NU + 1), gq);
+            double dt;
+            if (NCT > 0) {          // compile-time N: coordinates / basis table / gradients in registers
+                constexpr int NL = (NCT > 0 ? NCT : 1) * D;
+                double xl[NL], dl[NL], gl[NL];
+#pragma unroll
+                for (int i = 0; i < NL; ++i) { xl[i] = xe[i]; dl[i] = s_dphi[(size_t)q * (NU + 1) + i]; }
+                dt = shape_gradients<(NCT > 0 ? NCT : 1), D>(xl, dl, gl);
+#pragma unroll
+                for (int i = 0; i < NL; ++i) gq[i] = gl[i];
+            } else {
+                dt = shape_gradients_rt<D>(N, xe, s_dphi + (size_t)q * (NU + 1), gq);
+            }
             wdet[q] = dt * b.W[q];
             const double* mpq = mp + (int64_t)q * qs;
             if (iso_fast) {
@@ -203,7 +214,7 @@ __global__ void __launch_bounds__(128) k_tangent_iso(feb200_batch b, int epb, in
         const int64_t e = e0 + e_l;
         const bool active = (e_l < epb) && (e < b.E);
         __syncthreads();
-        stage_geometry<D>(b, N, e_l, a, e, active, x_vd, u, mask, values, s_dphi, s_el, per_el, 2, true);
+        stage_geometry<D, N>(b, N, e_l, a, e, active, x_vd, u, mask, values, s_dphi, s_el, per_el, 2, true);
         double acc[N][D2];
 #pragma unroll
         for (int bn = 0; bn < N; ++bn)
@@ -314,7 +325,7 @@ __global__ void k_tangent_general_ct(feb200_batch b, int epb, int per_el, const 
         const int64_t e = e0 + e_l;
         const bool active = (e_l < epb) && (e < b.E);
         __syncthreads();
-        stage_geometry<D>(b, N, e_l, a, e, active, x_vd, u, mask, values, s_dphi, s_el, per_el, D4, false);
+        stage_geometry<D, N>(b, N, e_l, a, e, active, x_vd, u, mask, values, s_dphi, s_el, per_el, D4, false);
         if (!active) continue;
         const double* g = s_el + (size_t)e_l * per_el + 2 * NU;
         const double* wdet = g + (size_t)Q * (NU + 1);
