@@ -17,14 +17,27 @@
 namespace feb {
 
 // Final store of one vertex's row panel from the shared-memory accumulators (panel layout), with the
-// optional fused Dirichlet elimination (apply_dirichlet_bcs_lhs, sparse_matrix.py:157-184).
+// optional fused Dirichlet elimination (apply_dirichlet_bcs_lhs, sparse_matrix.py:157-184).  The constraint
+// flags of the <= deg neighbours are gathered once per vertex into `flags` (per-warp shared memory: bit j =
+// component j constrained, bit 7 = the neighbour is the row vertex itself), not once per matrix entry.
 template <int U>
 __device__ __forceinline__ void store_panel(int lane, int64_t a, int deg, int64_t p0, const double* acc,
                                             double* __restrict__ values, int accumulate,
-                                            const int32_t* __restrict__ nindices, const double* __restrict__ mask) {
+                                            const int32_t* __restrict__ nindices, const double* __restrict__ mask,
+                                            unsigned char* flags) {
     constexpr int U2 = U * U;
     const int row_len = U * deg;
     double* dst = values + (int64_t)U2 * p0;
+    if (mask) {
+        for (int r = lane; r < deg; r += 32) {
+            const int64_t colv = nindices[p0 + r];
+            unsigned int f = (colv == a) ? 0x80u : 0u;
+#pragma unroll
+            for (int j = 0; j < U; ++j) f |= (mask[colv * U + j] != 0.0) ? (1u << j) : 0u;
+            flags[r] = (unsigned char)f;
+        }
+        __syncwarp();
+    }
 #pragma unroll
     for (int i = 0; i < U; ++i) {                       // row by row: no division by the run-time row length
         const bool rm = mask ? (mask[a * U + i] != 0.0) : false;
@@ -34,9 +47,9 @@ __device__ __forceinline__ void store_panel(int lane, int64_t a, int deg, int64_
             if (accumulate) v += dst[t];
             if (mask) {
                 const int r = c / U, j = c - r * U;
-                const int64_t colv = nindices[p0 + r];
-                const bool cm = mask[colv * U + j] != 0.0;
-                if (rm || cm) v = (rm && colv == a && i == j) ? 1.0 : 0.0;
+                const unsigned int f = flags[r];
+                const bool cm = (f >> j) & 1u;
+                if (rm || cm) v = (rm && (f & 0x80u) && i == j) ? 1.0 : 0.0;
             }
             dst[t] = v;
         }
@@ -54,6 +67,7 @@ __global__ void k_assemble_csr(const unsigned long long* __restrict__ row_ind, c
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     double* acc = smem + (size_t)warp * max_deg * U2;
+    unsigned char* flags = reinterpret_cast<unsigned char*>(smem + (size_t)wpb * max_deg * U2) + (size_t)warp * ((max_deg + 7) & ~7);
     const int items = N * U;                                   // (block, row-of-block) items per slot chunk
     for (int64_t a = (int64_t)blockIdx.x * wpb + warp; a < V; a += (int64_t)gridDim.x * wpb) {
         const int64_t p0 = nindptr[a];
@@ -74,7 +88,7 @@ __global__ void k_assemble_csr(const unsigned long long* __restrict__ row_ind, c
             }
             __syncwarp();
         }
-        store_panel<U>(lane, a, deg, p0, acc, values, accumulate, nindices, mask);
+        store_panel<U>(lane, a, deg, p0, acc, values, accumulate, nindices, mask, flags);
         __syncwarp();
     }
 }
@@ -95,6 +109,7 @@ __global__ void __launch_bounds__(256, 4) k_assemble_csr_pre(const unsigned long
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     double* acc = smem + (size_t)warp * max_deg * U2;
+    unsigned char* flags = reinterpret_cast<unsigned char*>(smem + (size_t)wpb * max_deg * U2) + (size_t)warp * ((max_deg + 7) & ~7);
     const int items = N * U;
     const bool has_item = lane < items;
     const int bn = lane / U, i = lane - bn * U;
@@ -130,7 +145,7 @@ __global__ void __launch_bounds__(256, 4) k_assemble_csr_pre(const unsigned long
                 __syncwarp();
             }
         }
-        store_panel<U>(lane, a, deg, p0, acc, values, accumulate, nindices, mask);
+        store_panel<U>(lane, a, deg, p0, acc, values, accumulate, nindices, mask, flags);
         __syncwarp();
     }
 }
@@ -238,7 +253,7 @@ int feb200_assemble_csr(feb200_stream s, const feb200_batch_map* map, int64_t V,
     const unsigned long long* ri = reinterpret_cast<const unsigned long long*>(map->row_ind);
     const unsigned long long* ci = reinterpret_cast<const unsigned long long*>(map->col_ind);
     int wpb = 8;
-    size_t per_warp = (size_t)max_deg * U * U * sizeof(double);
+    size_t per_warp = (size_t)max_deg * U * U * sizeof(double) + (size_t)((max_deg + 7) & ~7);
     while (wpb > 1 && per_warp * wpb > 64 * 1024) wpb >>= 1;
     const size_t smem = per_warp * wpb;
     FEB_REQUIRE(smem <= 200 * 1024, FEB200_ERR_CAPACITY, "assemble_csr: vertex degree %d needs %zu bytes of shared memory", max_deg, smem);
