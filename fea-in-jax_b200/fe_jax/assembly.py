@@ -399,16 +399,18 @@ def _assemble_values(element_residual_func, ebc, assembly_map_b, u, mask=None, v
 
 
 def _vertex_flags(ebc, mask):
-    """uint8 per vertex, bit j set when DoF U*v+j is constrained (input of the fused Dirichlet elimination);
-    cached per mask tensor."""
-    key = ("_vflags", mask.data_ptr(), mask._version)
-    hit = ebc._scratch.get("_vflags")
-    if hit is not None and hit[0] == key:
+    """uint8 per vertex, bit j set when DoF U*v+j is constrained (input of the fused Dirichlet elimination).
+    Cached on the mask tensor object itself (invalidated by in-place modification through `_version`)."""
+    hit = getattr(mask, "_feb200_vflags", None)
+    if hit is not None and hit[0] == mask._version:
         return hit[1]
     U = ebc.U[0]
     bits = torch.tensor([1 << j for j in range(U)], dtype=torch.int32, device=mask.device)
     flags = ((mask.view(-1, U) != 0).to(torch.int32) * bits).sum(dim=1).to(torch.uint8).contiguous()
-    ebc._scratch["_vflags"] = (key, flags)
+    try:
+        mask._feb200_vflags = (mask._version, flags)
+    except AttributeError:
+        pass
     return flags
 
 
