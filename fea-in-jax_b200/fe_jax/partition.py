@@ -141,36 +141,33 @@ class TorchDistComm:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
 
 
-_HALO_CACHE = {}
-
-
-def _halo_meta(rank, nb):
-    """(touched vertex ids, True if some vertex is shared with more than one neighbour), cached per index set"""
-    key = (rank, tuple((p, idx.data_ptr(), int(idx.shape[0])) for p, idx in sorted(nb.items())))
-    hit = _HALO_CACHE.get(key)
-    if hit is None:
-        allidx = torch.cat([idx for idx in nb.values()])
-        touched = allidx.unique()
-        hit = (touched, bool(touched.shape[0] != allidx.shape[0]))
-        _HALO_CACHE[key] = hit
-    return hit
+def halo_meta(nb):
+    """(touched vertex ids, True if some vertex is shared with more than one neighbour) for one rank's index sets"""
+    if not nb:
+        return None, False
+    allidx = torch.cat([idx for idx in nb.values()])
+    touched = allidx.unique()
+    return touched, bool(touched.shape[0] != allidx.shape[0])
 
 
 def halo_sum(comm, meshes_idx, vectors, U):
     """In place: every interface DoF becomes the sum of the partial values of all ranks sharing it, added in
-    ascending rank order (identical bits on every sharer).  meshes_idx[i] = (rank, {p: local vertex ids (tensor)}).
+    ascending rank order (identical bits on every sharer).  meshes_idx[i] = (rank, {p: local vertex ids (tensor)}
+    [, halo_meta(...)]): the optional third entry avoids recomputing the interface bookkeeping on every call.
     When every interface vertex has exactly two sharers (slab partitions) the sum is own + received, which is
     already order independent, so the received values are simply added."""
     send = []
-    for (rank, nb), v in zip(meshes_idx, vectors):
+    for entry, v in zip(meshes_idx, vectors):
+        nb = entry[1]
         v3 = v.view(-1, U)
         send.append({p: v3[idx] for p, idx in nb.items()})
     recv = comm.exchange(send)
-    for (rank, nb), v, rcv, snd in zip(meshes_idx, vectors, recv, send):
+    for entry, v, rcv, snd in zip(meshes_idx, vectors, recv, send):
+        rank, nb = entry[0], entry[1]
         if not nb:
             continue
         v3 = v.view(-1, U)
-        touched, multi = _halo_meta(rank, nb)
+        touched, multi = entry[2] if len(entry) > 2 else halo_meta(nb)
         if not multi:
             for p in sorted(nb):
                 v3.index_add_(0, nb[p], rcv[p])
@@ -215,7 +212,7 @@ class RankProblem:
             owned = torch.from_numpy(lm.owned).to(device)
             self.weights = owned.to(torch.float64).repeat_interleave(self.U).contiguous()
             self.nb = {p: torch.from_numpy(np.asarray(idx)).to(device) for p, idx in lm.neighbours.items()}
-            self.idx = (lm.rank, self.nb)
+            self.idx = (lm.rank, self.nb, halo_meta(self.nb))
 
 
 class DistributedProblem:
