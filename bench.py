@@ -300,7 +300,7 @@ def main():
     Rtmp = torch.empty(F, dtype=torch.float64, device=dev)
     row = maps[0].indptr.reshape(-1).view(torch.int64)
     col = maps[0].indices.reshape(-1).view(torch.int64)
-    fused = plan.fused_plan(ebc, 0) if bstruct.layout != _lib.LAYOUT_EQM else None
+    fused = plan.fused_plan(ebc, 0)
     from fe_jax.assembly import _vertex_flags
     vflags = _vertex_flags(ebc, mask)
     kernels = {
@@ -396,10 +396,10 @@ def main():
         total_E = E * world
         value = total_E / (ms_step * 1e-3)
         # algorithmic bytes (the slot map is 2 bytes per node pair here):
-        #   Jacobian assembly kernel  B_J = 8 nnz + 2 N^2 E + 4 N E + 8 D V
+        #   Jacobian assembly kernel  B_J = 8 nnz + 2 N^2 E + 4 N E + 8 D V + 8 n_mp (material parameters)
         #   whole assembly pass       B_A = B_J + 8 F (u) + 8 F (R) + 16 F (mask, values) + 8 n_mp
         n_mp = {"M": 2, "EM": 2 * E, "EQM": 16 * E}[args.layout]
-        bytes_J = 8 * nnz + 2 * 64 * E + 4 * 8 * E + 8 * 3 * V
+        bytes_J = 8 * nnz + 2 * 64 * E + 4 * 8 * E + 8 * 3 * V + 8 * n_mp
         alg_bytes = bytes_J + 8 * F + 8 * F + 16 * F + 8 * n_mp
         if "assemble_fused_hex8" in kernel_ms:
             dom, dom_ms = "feb200_assemble_fused_hex8 (k_fused_hex8_iso)", kernel_ms["assemble_fused_hex8"]

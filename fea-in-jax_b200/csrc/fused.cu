@@ -49,7 +49,7 @@ static inline FusedSmem fused_layout(int tn_cap, int te_cap) {
     L.tn_cap = tn_cap;
     L.te_cap = te_cap;
     L.off_g = 0;
-    size_t g_doubles = (size_t)te_cap * EL_STRIDE + (size_t)te_cap * WD_STRIDE;    // G + wdet
+    size_t g_doubles = (size_t)te_cap * EL_STRIDE + 2 * (size_t)te_cap * WD_STRIDE;    // G + wdet + lambda/mu ratio
     g_doubles = (g_doubles + 1) & ~(size_t)1;
     L.off_ws = g_doubles * 8;
     size_t ws_doubles = (size_t)FUSED_WARPS * WS_DOUBLES;                          // xs (te*25) aliases the start
@@ -81,6 +81,7 @@ struct TilePrefetch {
     int32_t vtx[PF];         // B
     int32_t nbr[PN];         // B
     int32_t item_el;         // B
+    double mpq[PF][2];       // B   PERQ: (E, nu) of quadrature point (tid + j*THREADS) & 7 of element el[j]
     double x[PF][3];         // C
     uint32_t flg;            // C   PN flags packed
     uint4 rk8;               // C
@@ -91,14 +92,17 @@ struct TilePrefetch {
 //   B  lane = neighbour rank r adds its <= 8 contributions in ascending slot order, eliminates, stores
 // UNIFORM (material layout (M,): one lambda, mu for the batch): the blocks S_ab are summed first and
 // K = lam S + mu S^T + mu tr(S) I is applied once per CSR block instead of once per contribution.
-template <bool ELIM, bool UNIFORM>
+// PERQ (material layout (E,Q,M): lambda, mu per quadrature point): with m_q = detJ W mu g_a and l_q = (lambda/mu) m_q,
+// K_ab = S_l + S_m^T + tr(S_m) I where S_l = sum_q l_q (x) g_b and S_m = sum_q m_q (x) g_b.
+template <bool ELIM, bool UNIFORM, bool PERQ>
 __global__ void __launch_bounds__(FUSED_THREADS, FEB_FUSED_MINBLOCKS)
 k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const double* __restrict__ x_vd,
                  const uint16_t* __restrict__ slot_rank, const int32_t* __restrict__ nindices,
                  const uint8_t* __restrict__ vflags, double* __restrict__ values) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* G = reinterpret_cast<double*>(smem_raw + L.off_g);              // [le] EL_STRIDE : [n] G_STRIDE : g[q][3]
-    double* wdet = G + (size_t)L.te_cap * EL_STRIDE;                        // [le][q]
+    double* wdet = G + (size_t)L.te_cap * EL_STRIDE;                        // [le][q]  (PERQ: detJ*W*mu)
+    double* rlm = wdet + (size_t)L.te_cap * WD_STRIDE;                      // [le][q]  PERQ only: lambda / mu
     double* wstage = reinterpret_cast<double*>(smem_raw + L.off_ws);        // [warp][k][b][9]
     double* xs = wstage;                                                    // [le] XS_STRIDE : [n][3]   (P0-P1 only)
     double* s_dphi = reinterpret_cast<double*>(smem_raw + L.off_dphi);      // [q] DPHI_STRIDE : [n][3]
@@ -144,8 +148,14 @@ k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const doub
     auto level_b = [&](int tile) {
         const int e0 = plan.tile_elem_ptr[tile];
 #pragma unroll
-        for (int j = 0; j < PF; ++j)
+        for (int j = 0; j < PF; ++j) {
             pf.vtx[j] = (pf.el[j] >= 0) ? b.conn[(int64_t)pf.el[j] * 8 + ((tid + j * FUSED_THREADS) & 7)] : -1;
+            if (PERQ && pf.el[j] >= 0) {
+                const double* mp = b.mp + ((int64_t)pf.el[j] * 8 + ((tid + j * FUSED_THREADS) & 7)) * b.M;
+                pf.mpq[j][0] = mp[0];
+                pf.mpq[j][1] = mp[1];
+            }
+        }
 #pragma unroll
         for (int j = 0; j < PN; ++j) {
             const int r = (tid + j * FUSED_THREADS) % FUSED_MAXDEG;
@@ -188,7 +198,7 @@ k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const doub
                 const int le = i >> 3, n = i & 7;
 #pragma unroll
                 for (int d = 0; d < 3; ++d) xs[le * XS_STRIDE + n * 3 + d] = pf.x[j][d];
-                if (n == 0) {
+                if (!PERQ && n == 0) {
                     int qs;
                     const double* mp = mp_of(b, pf.el[j], qs);
                     double lam, mu;
@@ -224,11 +234,21 @@ k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const doub
             }
         }
         // ---- P1: geometry, one thread per (element, quadrature point)
-        for (int i = tid; i < TE * 8; i += FUSED_THREADS) {
+#pragma unroll
+        for (int jj = 0; jj < PF; ++jj) {
+            const int i = tid + jj * FUSED_THREADS;
+            if (i >= TE * 8) break;
             const int le = i >> 3, q = i & 7;
             double g[24];
             const double dt = shape_gradients<8, 3>(xs + le * XS_STRIDE, s_dphi + q * DPHI_STRIDE, g);
-            wdet[le * WD_STRIDE + q] = dt * b.W[q];
+            if (PERQ) {
+                double lam, mu;
+                isotropic_lame<3>(pf.mpq[jj], lam, mu);
+                wdet[le * WD_STRIDE + q] = dt * b.W[q] * mu;
+                rlm[le * WD_STRIDE + q] = lam / mu;
+            } else {
+                wdet[le * WD_STRIDE + q] = dt * b.W[q];
+            }
 #pragma unroll
             for (int n = 0; n < 8; ++n)
 #pragma unroll
@@ -260,11 +280,41 @@ k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const doub
 #pragma unroll
                             for (int d = 0; d < 3; ++d) wga[q][d] = w[q] * tmp[q * 3 + d];
                     }
-                    const double lam = lm[le * 2], mu = lm[le * 2 + 1];
+                    const double lam = PERQ ? 0.0 : lm[le * 2], mu = PERQ ? 0.0 : lm[le * 2 + 1];
+                    const double* rl = rlm + le * WD_STRIDE;
 #pragma unroll
                     for (int bi = 0; bi < 2; ++bi) {
                         const int bn = 2 * bp + bi;
                         const double2* rec = reinterpret_cast<const double2*>(G + (size_t)le * EL_STRIDE + bn * G_STRIDE);
+                        double* dst = ws + (k * 8 + bn) * 9 + (k >> 1);
+                        if (PERQ) {
+                            double Sl[9], Sm[9];
+#pragma unroll
+                            for (int c = 0; c < 9; ++c) { Sl[c] = 0.0; Sm[c] = 0.0; }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const double2 v0 = rec[3 * j], v1 = rec[3 * j + 1], v2 = rec[3 * j + 2];
+                                const double gb0[3] = {v0.x, v0.y, v1.x}, gb1[3] = {v1.y, v2.x, v2.y};
+#pragma unroll
+                                for (int i = 0; i < 3; ++i) {
+                                    const double m0 = wga[2 * j][i], m1 = wga[2 * j + 1][i];
+                                    const double l0 = rl[2 * j] * m0, l1 = rl[2 * j + 1] * m1;
+#pragma unroll
+                                    for (int l = 0; l < 3; ++l) {
+                                        Sm[i * 3 + l] += m0 * gb0[l];
+                                        Sm[i * 3 + l] += m1 * gb1[l];
+                                        Sl[i * 3 + l] += l0 * gb0[l];
+                                        Sl[i * 3 + l] += l1 * gb1[l];
+                                    }
+                                }
+                            }
+                            const double tr = Sm[0] + Sm[4] + Sm[8];
+#pragma unroll
+                            for (int d = 0; d < 3; ++d)
+#pragma unroll
+                                for (int kk = 0; kk < 3; ++kk) dst[d * 3 + kk] = Sl[d * 3 + kk] + Sm[kk * 3 + d] + (d == kk ? tr : 0.0);
+                            continue;
+                        }
                         double S[9];
 #pragma unroll
                         for (int c = 0; c < 9; ++c) S[c] = 0.0;
@@ -280,7 +330,6 @@ k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const doub
                                     S[i * 3 + l] += wga[2 * j + 1][i] * gb1[l];
                                 }
                         }
-                        double* dst = ws + (k * 8 + bn) * 9 + (k >> 1);
                         if (UNIFORM) {
 #pragma unroll
                             for (int c = 0; c < 9; ++c) dst[c] = S[c];
@@ -368,8 +417,8 @@ int feb200_assemble_fused_hex8(feb200_stream s, const feb200_batch* bp, const fe
                 "assemble_fused_hex8: null pointer");
     const feb200_batch& b = *bp;
     FEB_REQUIRE(b.N == 8 && b.Q == 8 && b.D == 3, FEB200_ERR_UNSUPPORTED, "assemble_fused_hex8: needs hex8 with 8 quadrature points");
-    FEB_REQUIRE(b.kind == FEB200_KIND_LINEAR && b.material == FEB200_MAT_ISOTROPIC && b.layout != FEB200_LAYOUT_EQM,
-                FEB200_ERR_UNSUPPORTED, "assemble_fused_hex8: needs linear isotropic material, constant per element");
+    FEB_REQUIRE(b.kind == FEB200_KIND_LINEAR && b.material == FEB200_MAT_ISOTROPIC, FEB200_ERR_UNSUPPORTED,
+                "assemble_fused_hex8: needs the linear isotropic material");
     FEB_REQUIRE(b.conn && b.dphi && b.W && b.mp && b.M >= 2, FEB200_ERR_INVALID, "assemble_fused_hex8: bad batch");
     FEB_REQUIRE(plan->tile_node_ptr && plan->tile_nodes && plan->tile_elem_ptr && plan->tile_elems && plan->tile_item_ptr &&
                     plan->tile_items && plan->tile_node_p0 && plan->tile_node_meta && plan->n_tiles >= 0,
@@ -384,10 +433,14 @@ int feb200_assemble_fused_hex8(feb200_stream s, const feb200_batch* bp, const fe
     (void)row_ind;
     (void)nindptr;
     int grid = plan->n_tiles < sm_count() * FEB_FUSED_MINBLOCKS ? plan->n_tiles : sm_count() * FEB_FUSED_MINBLOCKS;
-    const bool uniform = (b.layout == FEB200_LAYOUT_M);
+    const bool uniform = (b.layout == FEB200_LAYOUT_M), perq = (b.layout == FEB200_LAYOUT_EQM);
 #define FEB_FUSED_LAUNCH(EL, UN)                                                                                       \
-    {                                                                                                                  \
-        auto kern = k_fused_hex8_iso<EL, UN>;                                                                          \
+    if (perq) {                                                                                                        \
+        auto kern = k_fused_hex8_iso<EL, false, true>;                                                                 \
+        FEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));               \
+        kern<<<grid, FUSED_THREADS, L.total, st>>>(b, *plan, L, x_vd, slot_rank, nindices, vertex_flags, values);      \
+    } else {                                                                                                           \
+        auto kern = k_fused_hex8_iso<EL, UN, false>;                                                                   \
         FEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));               \
         kern<<<grid, FUSED_THREADS, L.total, st>>>(b, *plan, L, x_vd, slot_rank, nindices, vertex_flags, values);      \
     }

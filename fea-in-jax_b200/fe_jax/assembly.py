@@ -378,9 +378,8 @@ def _assemble_values(element_residual_func, ebc, assembly_map_b, u, mask=None, v
     vals = out if out is not None else torch.empty(pat.nnz, dtype=torch.float64, device=u.device)
     for i in range(ebc.B):
         b = ebc._batch_struct(i, res.kind)
-        # fused path: linear isotropic hex8, material constant per element, single batch (tangent independent of u)
-        if (b.kind == _lib.KIND_LINEAR and b.material == _lib.MAT_ISOTROPIC and b.layout != _lib.LAYOUT_EQM
-                and plan.fused_plan(ebc, i) is not None):
+        # fused path: linear isotropic hex8 (any material layout), single batch (tangent independent of u)
+        if (b.kind == _lib.KIND_LINEAR and b.material == _lib.MAT_ISOTROPIC and plan.fused_plan(ebc, i) is not None):
             fp = plan.fused_plan(ebc, i)
             flags = _vertex_flags(ebc, mask) if (eliminate and mask is not None) else None
             _lib.call("feb200_assemble_fused_hex8", b, fp.struct, _lib.ptr(ebc._vertices), _lib.ptr(plan._keep[i][0]),
