@@ -309,7 +309,13 @@ def main():
         "scatter_sum": lambda: _lib.call("feb200_scatter_sum", _lib.ptr(row), _lib.ptr(col), V, 3, _lib.ptr(R_e),
                                          _lib.ptr(Rtmp), 0, _lib.ptr(mask), _lib.ptr(values), _lib.ptr(u)),
     }
-    if fused is not None:
+    use_mma = (fused is not None and bstruct.layout != _lib.LAYOUT_EQM
+               and os.environ.get("FEB200_FUSED_IMPL", "mma") == "mma")
+    if use_mma:
+        kernels["assemble_fused_hex8"] = lambda: _lib.call(
+            "feb200_assemble_fused_hex8_mma", bstruct, fused.struct, _lib.ptr(ebc._vertices), _lib.ptr(plan.slot_rank[0]),
+            _lib.ptr(pat.nindices), _lib.ptr(vflags), _lib.ptr(J_vals))
+    elif fused is not None:
         kernels["assemble_fused_hex8"] = lambda: _lib.call(
             "feb200_assemble_fused_hex8", bstruct, fused.struct, _lib.ptr(ebc._vertices), _lib.ptr(row),
             _lib.ptr(plan.slot_rank[0]), _lib.ptr(pat.nindptr), _lib.ptr(pat.nindices), _lib.ptr(vflags), _lib.ptr(J_vals))
@@ -402,7 +408,9 @@ def main():
         bytes_J = 8 * nnz + 2 * 64 * E + 4 * 8 * E + 8 * 3 * V + 8 * n_mp
         alg_bytes = bytes_J + 8 * F + 8 * F + 16 * F + 8 * n_mp
         if "assemble_fused_hex8" in kernel_ms:
-            dom, dom_ms = "feb200_assemble_fused_hex8 (k_fused_hex8_iso)", kernel_ms["assemble_fused_hex8"]
+            dom = ("feb200_assemble_fused_hex8_mma (k_fused_hex8_mma)" if use_mma
+                   else "feb200_assemble_fused_hex8 (k_fused_hex8_iso)")
+            dom_ms = kernel_ms["assemble_fused_hex8"]
         else:
             dom = "element_tangent + assemble_csr (two-pass assembly)"
             dom_ms = kernel_ms["element_tangent"] + kernel_ms["assemble_csr"]
@@ -410,7 +418,7 @@ def main():
         traffic = None
         try:        # dram bytes of the dominant kernel from the committed ncu --set full capture of this configuration
             with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-                traffic = json.load(f).get(f"fused_n{n}_{args.layout}") if "assemble_fused_hex8" in kernel_ms else None
+                traffic = json.load(f).get(f"fused{'_mma' if use_mma else ''}_n{n}_{args.layout}") if "assemble_fused_hex8" in kernel_ms else None
         except Exception:
             pass
         spmv_bytes = 8 * nnz + 4 * (nnz // 9) + 8 * (V + 1) + 16 * F

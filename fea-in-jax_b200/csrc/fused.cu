@@ -313,8 +313,7 @@ k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const doub
                             for (int d = 0; d < 3; ++d)
 #pragma unroll
                                 for (int kk = 0; kk < 3; ++kk) dst[d * 3 + kk] = Sl[d * 3 + kk] + Sm[kk * 3 + d] + (d == kk ? tr : 0.0);
-                            continue;
-                        }
+                        } else {
                         double S[9];
 #pragma unroll
                         for (int c = 0; c < 9; ++c) S[c] = 0.0;
@@ -340,6 +339,7 @@ k_fused_hex8_iso(feb200_batch b, feb200_fused_plan plan, FusedSmem L, const doub
 #pragma unroll
                                 for (int kk = 0; kk < 3; ++kk)
                                     dst[d * 3 + kk] = lam * S[d * 3 + kk] + mu * S[kk * 3 + d] + (d == kk ? tr : 0.0);
+                        }
                         }
                     }
                 }

@@ -382,6 +382,10 @@ def _assemble_values(element_residual_func, ebc, assembly_map_b, u, mask=None, v
         if (b.kind == _lib.KIND_LINEAR and b.material == _lib.MAT_ISOTROPIC and plan.fused_plan(ebc, i) is not None):
             fp = plan.fused_plan(ebc, i)
             flags = _vertex_flags(ebc, mask) if (eliminate and mask is not None) else None
+            if b.layout != _lib.LAYOUT_EQM and os.environ.get("FEB200_FUSED_IMPL", "mma") == "mma":
+                _lib.call("feb200_assemble_fused_hex8_mma", b, fp.struct, _lib.ptr(ebc._vertices),
+                          _lib.ptr(plan.slot_rank[i]), _lib.ptr(pat.nindices), _lib.ptr(flags), _lib.ptr(vals))
+                continue
             _lib.call("feb200_assemble_fused_hex8", b, fp.struct, _lib.ptr(ebc._vertices), _lib.ptr(plan._keep[i][0]),
                       _lib.ptr(plan.slot_rank[i]), _lib.ptr(pat.nindptr), _lib.ptr(pat.nindices),
                       _lib.ptr(flags), _lib.ptr(vals))

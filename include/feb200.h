@@ -175,6 +175,13 @@ size_t feb200_fused_smem_bytes(int32_t tn_cap, int32_t te_cap);
 int feb200_assemble_fused_hex8(feb200_stream s, const feb200_batch* b, const feb200_fused_plan* plan, const double* x_vd,
                                const uint64_t* row_ind, const uint16_t* slot_rank, const int64_t* nindptr,
                                const int32_t* nindices, const uint8_t* vertex_flags, double* values);
+/* The same contract (same plan, same outputs) with the block products of an element evaluated as one 24 x 24 x 8
+ * FP64 tensor-core product (mma.sync m8n8k4) instead of 3x3 blocks one by one; material layouts (M,) and (E,M).
+ * The per-point layout (E,Q,M) stays on feb200_assemble_fused_hex8. */
+size_t feb200_fused_mma_smem_bytes(int32_t tn_cap, int32_t te_cap);
+int feb200_assemble_fused_hex8_mma(feb200_stream s, const feb200_batch* b, const feb200_fused_plan* plan, const double* x_vd,
+                                   const uint16_t* slot_rank, const int32_t* nindices, const uint8_t* vertex_flags,
+                                   double* values);
 
 /* apply_dirichlet_bcs_lhs on the node-pattern CSR (sparse_matrix.py:157-184). mask: (U*V) 0/1 doubles. */
 int feb200_dirichlet_lhs(feb200_stream s, int64_t V, int32_t U, const int64_t* nindptr, const int32_t* nindices,
