@@ -19,17 +19,17 @@
 #include "common.cuh"
 #include "element_math.cuh"
 
-#ifndef FEB_MM_COALESCED
-#define FEB_MM_COALESCED 0
-#endif
 #ifndef FEB_MM_LEVELB_EARLY
 #define FEB_MM_LEVELB_EARLY 0
 #endif
 #ifndef FEB_MM_LEVELC_AFTER
-#define FEB_MM_LEVELC_AFTER 2        /* B phase: issue the coordinate prefetch after this many vertices of the warp */
+#define FEB_MM_LEVELC_AFTER 1        /* B phase: issue the coordinate prefetch after this many vertices of the warp */
 #endif
-#ifndef FEB_MM_BUNROLL
-#define FEB_MM_BUNROLL 1
+#ifndef FEB_MM_ZEROREAD
+#define FEB_MM_ZEROREAD 0
+#endif
+#ifndef FEB_MM_BV
+#define FEB_MM_BV 2                  /* vertices a warp of phase B works on at a time */
 #endif
 #ifndef FEB_MM_GEOM128
 #define FEB_MM_GEOM128 1
@@ -37,7 +37,7 @@
 
 namespace feb {
 
-constexpr int MM_BUNROLL = FEB_MM_BUNROLL;
+constexpr int MM_BV = FEB_MM_BV;
 constexpr int MM_WARPS = 8;
 constexpr int MM_THREADS = MM_WARPS * 32;
 constexpr int MM_MAXVAL = 8;             // incident slots per vertex
@@ -405,96 +405,109 @@ k_fused_hex8_mma(feb200_batch b, feb200_fused_plan plan, MmaSmem L, const double
             if (has_next && !fetched_b) level_b(nxt);
         }
         __syncthreads();                                     // all block rows staged
-        // ---- B: warp per vertex, lane = CSR block rank
+        // ---- B: lane = CSR block rank; a warp works on MM_BV vertices at a time (independent instruction streams:
+        //         the phase is bound by dependent-issue latency, not by any pipe)
         bool fetched_c = false;
-        double* ob_base = gw + (size_t)warp * MM_GROUP * MM_EL;           // free in this phase: output transposition buffer
-        int flip = 0, n_done = 0;
-#pragma unroll MM_BUNROLL
-        for (int a = warp; a < TN; a += MM_WARPS, flip ^= 1) {
-            const int meta = meta_s[a];
-            const int deg = meta & 0xff;
+        int n_done = 0;
+        for (int a0 = warp; a0 < TN; a0 += MM_BV * MM_WARPS) {
             const int r = lane;
-            const unsigned int src0 = tbl[a * MM_MAXDEG + r];
-            const uint2 tk = *reinterpret_cast<const uint2*>(itof_s + a * MM_MAXVAL);
-            tbl[a * MM_MAXDEG + r] = 0xffffffffu;            // leave the table cleared for the next tile
-            double acc[9], accl[9];
+            int av[MM_BV], meta[MM_BV];
+            unsigned int src[MM_BV];
+            uint2 tk[MM_BV];
+            double acc[MM_BV][9], accl[UNIFORM ? 1 : MM_BV][9];
 #pragma unroll
-            for (int c = 0; c < 9; ++c) { acc[c] = 0.0; accl[c] = 0.0; }
-            unsigned int src = src0;
+            for (int v = 0; v < MM_BV; ++v) {
+                const int a = a0 + v * MM_WARPS;
+                av[v] = a < TN ? a : -1;
+                const int as = a < TN ? a : a0;
+                meta[v] = meta_s[as];
+                src[v] = tbl[as * MM_MAXDEG + r];
+                tk[v] = *reinterpret_cast<const uint2*>(itof_s + as * MM_MAXVAL);
 #pragma unroll
-            for (int k = 0; k < MM_MAXVAL; ++k) {
-                const unsigned int bsel = src & 0xfu;
-                src >>= 4;
-                const int t = (int)(((k < 4 ? tk.x : tk.y) >> (8 * (k & 3))) & 0xffu);
-                const double* sp = (bsel != 0xfu) ? stage + (size_t)t * MM_IS + bsel * 3 : zero_s;
-                if (UNIFORM) {
-#pragma unroll
-                    for (int i = 0; i < 3; ++i)
-#pragma unroll
-                        for (int j = 0; j < 3; ++j) acc[i * 3 + j] += sp[i * 24 + j];
-                } else {
-                    const double rho = (bsel != 0xfu) ? xs[(itw_s[t] & 0xfffu) * MM_XS + 25] : 0.0;
-#pragma unroll
-                    for (int i = 0; i < 3; ++i)
-#pragma unroll
-                        for (int j = 0; j < 3; ++j) {
-                            const double v = sp[i * 24 + j];
-                            acc[i * 3 + j] += v;
-                            accl[i * 3 + j] += rho * v;
-                        }
+                for (int c = 0; c < 9; ++c) {
+                    acc[v][c] = 0.0;
+                    if (!UNIFORM) accl[v][c] = 0.0;
                 }
             }
-            const int64_t p0 = p0_s[a];
-            const int row_len = 3 * deg;
-            double* ob = ob_base + flip * (9 * MM_MAXDEG);
-            if (r < deg) {
-                double K[9];
-                if (UNIFORM) {
-                    const double tr = u_mu * (acc[0] + acc[4] + acc[8]);
+            __syncwarp();
 #pragma unroll
-                    for (int d = 0; d < 3; ++d)
+            for (int v = 0; v < MM_BV; ++v)
+                if (av[v] >= 0) tbl[av[v] * MM_MAXDEG + r] = 0xffffffffu;      // leave the table cleared for the next tile
 #pragma unroll
-                        for (int kk = 0; kk < 3; ++kk)
-                            K[d * 3 + kk] = u_lam * acc[d * 3 + kk] + u_mu * acc[kk * 3 + d] + (d == kk ? tr : 0.0);
-                } else {
-                    const double tr = acc[0] + acc[4] + acc[8];
+            for (int k = 0; k < MM_MAXVAL; ++k) {
 #pragma unroll
-                    for (int d = 0; d < 3; ++d)
-#pragma unroll
-                        for (int kk = 0; kk < 3; ++kk) K[d * 3 + kk] = accl[d * 3 + kk] + acc[kk * 3 + d] + (d == kk ? tr : 0.0);
-                }
-                if (ELIM) {
-                    const unsigned int cfd = flg_s[a * MM_MAXDEG + r];
-                    const unsigned int cf = cfd & 7u, diag = cfd & 8u;
-                    const unsigned int rf = ((unsigned int)meta >> 16) & 7u;
-                    if (cf | rf) {
+                for (int v = 0; v < MM_BV; ++v) {
+                    const unsigned int bsel = (src[v] >> (4 * k)) & 0xfu;
+                    const int t = (int)(((k < 4 ? tk[v].x : tk[v].y) >> (8 * (k & 3))) & 0xffu);
+                    const bool on = (bsel != 0xfu) && (av[v] >= 0);
+#if FEB_MM_ZEROREAD
+                    const double* sp = on ? stage + (size_t)t * MM_IS + bsel * 3 : zero_s;
+#define MM_LD(x) (x)
+#else
+                    const double* sp = stage + (size_t)t * MM_IS + bsel * 3;       // absent contributions: predicated-off loads
+#define MM_LD(x) (on ? (x) : 0.0)
+#endif
+                    if (UNIFORM) {
 #pragma unroll
                         for (int i = 0; i < 3; ++i)
 #pragma unroll
-                            for (int j = 0; j < 3; ++j)
-                                if (((rf >> i) & 1u) || ((cf >> j) & 1u)) K[i * 3 + j] = (((rf >> i) & 1u) && diag && i == j) ? 1.0 : 0.0;
+                            for (int j = 0; j < 3; ++j) acc[v][i * 3 + j] += MM_LD(sp[i * 24 + j]);
+                    } else {
+                        const double rho = on ? xs[(itw_s[t] & 0xfffu) * MM_XS + 25] : 0.0;
+#pragma unroll
+                        for (int i = 0; i < 3; ++i)
+#pragma unroll
+                            for (int j = 0; j < 3; ++j) {
+                                const double val = MM_LD(sp[i * 24 + j]);
+                                acc[v][i * 3 + j] += val;
+                                accl[UNIFORM ? 0 : v][i * 3 + j] += rho * val;
+                            }
                     }
                 }
-#if FEB_MM_COALESCED
-#pragma unroll
-                for (int i = 0; i < 3; ++i)
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) ob[i * row_len + 3 * r + j] = K[i * 3 + j];
             }
-            __syncwarp();
-            {   // the vertex's panel rows are one contiguous run of 9 * deg doubles
-                double* dst = values + 9 * p0;
-                for (int idx = lane; idx < 3 * row_len; idx += 32) __stcs(dst + idx, ob[idx]);
-            }
-#else
-                double* dst = values + 9 * p0 + 3 * r;
 #pragma unroll
-                for (int i = 0; i < 3; ++i)
+            for (int v = 0; v < MM_BV; ++v) {
+                const int a = av[v];
+                const int deg = meta[v] & 0xff;
+                if (a >= 0 && r < deg) {
+                    const int64_t p0 = p0_s[a];
+                    const int row_len = 3 * deg;
+                    double K[9];
+                    if (UNIFORM) {
+                        const double tr = u_mu * (acc[v][0] + acc[v][4] + acc[v][8]);
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) __stcs(dst + (int64_t)i * row_len + j, K[i * 3 + j]);
+                        for (int d = 0; d < 3; ++d)
+#pragma unroll
+                            for (int kk = 0; kk < 3; ++kk)
+                                K[d * 3 + kk] = u_lam * acc[v][d * 3 + kk] + u_mu * acc[v][kk * 3 + d] + (d == kk ? tr : 0.0);
+                    } else {
+                        const double tr = acc[v][0] + acc[v][4] + acc[v][8];
+#pragma unroll
+                        for (int d = 0; d < 3; ++d)
+#pragma unroll
+                            for (int kk = 0; kk < 3; ++kk)
+                                K[d * 3 + kk] = accl[UNIFORM ? 0 : v][d * 3 + kk] + acc[v][kk * 3 + d] + (d == kk ? tr : 0.0);
+                    }
+                    if (ELIM) {
+                        const unsigned int cfd = flg_s[a * MM_MAXDEG + r];
+                        const unsigned int cf = cfd & 7u, diag = cfd & 8u;
+                        const unsigned int rf = ((unsigned int)meta[v] >> 16) & 7u;
+                        if (cf | rf) {
+#pragma unroll
+                            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                                for (int j = 0; j < 3; ++j)
+                                    if (((rf >> i) & 1u) || ((cf >> j) & 1u))
+                                        K[i * 3 + j] = (((rf >> i) & 1u) && diag && i == j) ? 1.0 : 0.0;
+                        }
+                    }
+                    double* dst = values + 9 * p0 + 3 * r;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) __stcs(dst + (int64_t)i * row_len + j, K[i * 3 + j]);
+                }
             }
-            (void)ob;
-#endif
             if (has_next && !fetched_c && ++n_done >= FEB_MM_LEVELC_AFTER) { level_c(); fetched_c = true; }
         }
         if (has_next && !fetched_c) level_c();

@@ -18,7 +18,11 @@ print("plan stats", fp.stats, "tn_cap", fp.tn_cap)
 u = torch.zeros(3 * Vx.shape[0], dtype=torch.float64, device="cuda")
 mask = torch.zeros_like(u); mask[:300] = 1.0
 out = torch.empty(plan.pattern.nnz, dtype=torch.float64, device="cuda")
+vals = torch.zeros_like(u)
+reps = int(os.environ.get("PF_REPS", "3"))
 for it in range(3):
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    _assemble_values(fj.linear_elasticity_residual, ebc, maps, u, mask, torch.zeros_like(u), out=out, eliminate=True)
-    torch.cuda.synchronize(); print("fused assemble ms", (time.perf_counter() - t0) * 1e3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(reps):
+        _assemble_values(fj.linear_elasticity_residual, ebc, maps, u, mask, vals, out=out, eliminate=True)
+    e1.record(); torch.cuda.synchronize(); print("fused assemble ms", e0.elapsed_time(e1) / reps)
