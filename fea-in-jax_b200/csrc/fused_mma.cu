@@ -28,28 +28,34 @@
 #ifndef FEB_MM_ZEROREAD
 #define FEB_MM_ZEROREAD 0
 #endif
+#ifndef FEB_MM_WARPS
+#define FEB_MM_WARPS 8
+#endif
+#ifndef FEB_MM_GROUP
+#define FEB_MM_GROUP 4               /* elements per warp step: 4 = lane (element, point); 2 = lane (element, point, node half) */
+#endif
+#ifndef FEB_MM_MINBLOCKS
+#define FEB_MM_MINBLOCKS 1           /* CTAs per SM (2 needs 16-vertex tiles: FEB200_FUSED_TN=16) */
+#endif
 #ifndef FEB_MM_BV
 #define FEB_MM_BV 2                  /* vertices a warp of phase B works on at a time */
-#endif
-#ifndef FEB_MM_GEOM128
-#define FEB_MM_GEOM128 1
 #endif
 
 namespace feb {
 
 constexpr int MM_BV = FEB_MM_BV;
-constexpr int MM_WARPS = 8;
+constexpr int MM_WARPS = FEB_MM_WARPS;
 constexpr int MM_THREADS = MM_WARPS * 32;
 constexpr int MM_MAXVAL = 8;             // incident slots per vertex
 constexpr int MM_MAXDEG = 32;            // CSR blocks per vertex row (lane each)
-constexpr int MM_GROUP = 4;              // elements per warp step: lane = (element, quadrature point)
+constexpr int MM_GROUP = FEB_MM_GROUP;     // elements per warp step
 constexpr int MM_KS = 104;               // doubles per k-step half of an element's fragment buffer: [row 0..23][4 points] + 8 (weights)
 constexpr int MM_EL = 212;               // doubles per element in the fragment buffer (2 * KS + 4): KS = 8, EL = 4 (mod 16) keeps the
                                          // geometry writes (lane = element, point) on distinct banks
 constexpr int MM_IS = 72;                // doubles per staged item: [i][b*3+j]
 constexpr int MM_XS = 26;                // doubles per element coordinate record: [n][3], mu, lambda/mu
 constexpr int MM_DPHI = 26;              // doubles per quadrature point in the basis table (24 used, 16-byte rows)
-constexpr int MM_PF = 3;                 // te_cap * 8 <= PF * THREADS   (te_cap <= 96)
+constexpr int MM_PF = (96 * 8 + MM_THREADS - 1) / MM_THREADS;   // te_cap * 8 <= PF * THREADS   (te_cap <= 96)
 constexpr int MM_PN = (MM_MAXDEG * 32 + MM_THREADS - 1) / MM_THREADS;
 
 struct MmaSmem {
@@ -145,6 +151,45 @@ __device__ __forceinline__ double hex8_gradients(const double* __restrict__ xe, 
     return dt;
 }
 
+// The same for the four nodes 4h .. 4h+3 only (lane = (element, point, node half) when a warp step covers two elements).
+__device__ __forceinline__ double hex8_gradients_half(const double* __restrict__ xe, const double* __restrict__ dq, int h,
+                                                      double (&g)[12]) {
+    const double2* x2 = reinterpret_cast<const double2*>(xe);
+    const double2* d2 = reinterpret_cast<const double2*>(dq);
+    double J[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+#pragma unroll
+    for (int hh = 0; hh < 4; ++hh) {
+        const double2 xa = x2[3 * hh], xb = x2[3 * hh + 1], xc = x2[3 * hh + 2];
+        const double2 da = d2[3 * hh], db = d2[3 * hh + 1], dc = d2[3 * hh + 2];
+        const double x[6] = {xa.x, xa.y, xb.x, xb.y, xc.x, xc.y};
+        const double d[6] = {da.x, da.y, db.x, db.y, dc.x, dc.y};
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int pp = 0; pp < 3; ++pp)
+#pragma unroll
+                for (int dd = 0; dd < 3; ++dd) J[pp][dd] += x[3 * m + dd] * d[3 * m + pp];
+    }
+    double Ji[3][3];
+    const double dt = inverse(J, Ji);
+    const double2* dh = d2 + 6 * h;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        const double2 da = dh[3 * hh], db = dh[3 * hh + 1], dc = dh[3 * hh + 2];
+        const double d[6] = {da.x, da.y, db.x, db.y, dc.x, dc.y};
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int dd = 0; dd < 3; ++dd) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int pp = 0; pp < 3; ++pp) sacc += Ji[dd][pp] * d[3 * m + pp];
+                g[(2 * hh + m) * 3 + dd] = sacc;
+            }
+    }
+    return dt;
+}
+
 // Row tiles 0..NMT-1 of one element: S rows of the in-tile vertices (slot s = row / 3, component i = row % 3).
 template <int NMT>
 __device__ __forceinline__ void element_rows(const double* __restrict__ Ge, const double (&Bf)[3][2], double w0, double w1,
@@ -185,7 +230,7 @@ __device__ __forceinline__ void element_rows(const double* __restrict__ Ge, cons
 }
 
 template <bool ELIM, bool UNIFORM>
-__global__ void __launch_bounds__(MM_THREADS, 1)
+__global__ void __launch_bounds__(MM_THREADS, FEB_MM_MINBLOCKS)
 k_fused_hex8_mma(feb200_batch b, feb200_fused_plan plan, MmaSmem L, const double* __restrict__ x_vd,
                  const uint16_t* __restrict__ slot_rank, const int32_t* __restrict__ nindices,
                  const uint8_t* __restrict__ vflags, double* __restrict__ values) {
@@ -359,23 +404,30 @@ k_fused_hex8_mma(feb200_batch b, feb200_fused_plan plan, MmaSmem L, const double
                 if (lane == 0) g_next = atomicAdd(ctr, 1);   // claimed one step ahead: the counter's latency is off the path
                 int my0 = 0, my1 = 0;                        // item range of element g*4 + (lane & 3)
                 {
-                    const int le = g * MM_GROUP + (lane & 3);
+                    const int le = g * MM_GROUP + (lane & (MM_GROUP - 1));
                     if (le < TE) { my0 = e0_s[le]; my1 = e1_s[le]; }
                 }
-                {   // geometry: lane = (element j, point q)
+                if (MM_GROUP == 4) {   // geometry: lane = (element j, point q)
                     const int j = lane >> 3, q = lane & 7, le = g * MM_GROUP + j;
                     if (le < TE) {
                         double gr[24];
                         const double* xe = xs + le * MM_XS;
-                        #if FEB_MM_GEOM128
                         const double dt = hex8_gradients(xe, s_dphi + q * MM_DPHI, gr);
-#else
-                        const double dt = shape_gradients<8, 3>(xe, s_dphi + q * MM_DPHI, gr);
-#endif
                         double* dst = Gw + j * MM_EL + (q >> 2) * MM_KS + (q & 3);
 #pragma unroll
                         for (int r = 0; r < 24; ++r) dst[r * 4] = gr[r];
                         dst[96] = UNIFORM ? dt * s_w[q] : dt * s_w[q] * xe[24];
+                    }
+                } else {               // lane = (element j, point q, node half h)
+                    const int j = lane >> 4, q = (lane >> 1) & 7, h = lane & 1, le = g * MM_GROUP + j;
+                    if (le < TE) {
+                        double gr[12];
+                        const double* xe = xs + le * MM_XS;
+                        const double dt = hex8_gradients_half(xe, s_dphi + q * MM_DPHI, h, gr);
+                        double* dst = Gw + j * MM_EL + (q >> 2) * MM_KS + (q & 3);
+#pragma unroll
+                        for (int r = 0; r < 12; ++r) dst[(12 * h + r) * 4] = gr[r];
+                        if (h == 0) dst[96] = UNIFORM ? dt * s_w[q] : dt * s_w[q] * xe[24];
                     }
                 }
                 __syncwarp();
@@ -544,7 +596,8 @@ int feb200_assemble_fused_hex8_mma(feb200_stream s, const feb200_batch* bp, cons
     const MmaSmem L = mma_layout(plan->tn_cap, plan->te_cap);
     FEB_REQUIRE(L.total <= 227 * 1024, FEB200_ERR_CAPACITY, "assemble_fused_hex8_mma: tile needs %zu bytes of shared memory", L.total);
     cudaStream_t st = as_stream(s);
-    const int grid = plan->n_tiles < sm_count() ? plan->n_tiles : sm_count();
+    const int max_grid = sm_count() * (L.total <= 113 * 1024 ? FEB_MM_MINBLOCKS : 1);
+    const int grid = plan->n_tiles < max_grid ? plan->n_tiles : max_grid;
     const bool uniform = (b.layout == FEB200_LAYOUT_M);
 #define FEB_MMA_LAUNCH(EL, UN)                                                                                         \
     {                                                                                                                  \
