@@ -37,6 +37,9 @@
 #ifndef FEB_MM_MINBLOCKS
 #define FEB_MM_MINBLOCKS 1           /* CTAs per SM (2 needs 16-vertex tiles: FEB200_FUSED_TN=16) */
 #endif
+#ifndef FEB_MM_TAIL2
+#define FEB_MM_TAIL2 1               /* finish phase A with 2-element steps */
+#endif
 #ifndef FEB_MM_BV
 #define FEB_MM_BV 2                  /* vertices a warp of phase B works on at a time */
 #endif
@@ -394,7 +397,15 @@ k_fused_hex8_mma(feb200_batch b, feb200_fused_plan plan, MmaSmem L, const double
         // ---- A: element groups -> staged block rows
         {
             double* Gw = gw + (size_t)warp * MM_GROUP * MM_EL;
-            const int n_groups = (TE + MM_GROUP - 1) / MM_GROUP;
+            // work units: full rounds of 4-element steps, then the remainder in 2-element steps (lane = element, point,
+            // node half) so that the last round, which not every warp takes part in, is short
+#if FEB_MM_TAIL2
+            const int n4 = (MM_GROUP == 4) ? ((TE / 4) / MM_WARPS) * MM_WARPS : 0;
+#else
+            const int n4 = (MM_GROUP == 4) ? (TE + 3) / 4 : 0;
+#endif
+            const int rest = TE - 4 * n4 > 0 ? TE - 4 * n4 : 0;
+            const int n_groups = n4 + (rest + 1) / 2;
             bool fetched_b = false;
             int g_next = 0;
             if (lane == 0) g_next = atomicAdd(ctr, 1);
@@ -402,14 +413,17 @@ k_fused_hex8_mma(feb200_batch b, feb200_fused_plan plan, MmaSmem L, const double
                 const int g = __shfl_sync(0xffffffffu, g_next, 0);
                 if (g >= n_groups) break;
                 if (lane == 0) g_next = atomicAdd(ctr, 1);   // claimed one step ahead: the counter's latency is off the path
-                int my0 = 0, my1 = 0;                        // item range of element g*4 + (lane & 3)
+                const bool four = g < n4;
+                const int le0 = four ? 4 * g : 4 * n4 + 2 * (g - n4);
+                const int n_el = min(four ? 4 : 2, TE - le0);
+                int my0 = 0, my1 = 0;                        // item range of element le0 + (lane & 3)
                 {
-                    const int le = g * MM_GROUP + (lane & (MM_GROUP - 1));
-                    if (le < TE) { my0 = e0_s[le]; my1 = e1_s[le]; }
+                    const int le = le0 + (lane & 3);
+                    if ((lane & 3) < n_el) { my0 = e0_s[le]; my1 = e1_s[le]; }
                 }
-                if (MM_GROUP == 4) {   // geometry: lane = (element j, point q)
-                    const int j = lane >> 3, q = lane & 7, le = g * MM_GROUP + j;
-                    if (le < TE) {
+                if (four) {            // geometry: lane = (element j, point q)
+                    const int j = lane >> 3, q = lane & 7, le = le0 + j;
+                    if (j < n_el) {
                         double gr[24];
                         const double* xe = xs + le * MM_XS;
                         const double dt = hex8_gradients(xe, s_dphi + q * MM_DPHI, gr);
@@ -419,8 +433,8 @@ k_fused_hex8_mma(feb200_batch b, feb200_fused_plan plan, MmaSmem L, const double
                         dst[96] = UNIFORM ? dt * s_w[q] : dt * s_w[q] * xe[24];
                     }
                 } else {               // lane = (element j, point q, node half h)
-                    const int j = lane >> 4, q = (lane >> 1) & 7, h = lane & 1, le = g * MM_GROUP + j;
-                    if (le < TE) {
+                    const int j = lane >> 4, q = (lane >> 1) & 7, h = lane & 1, le = le0 + j;
+                    if (j < n_el) {
                         double gr[12];
                         const double* xe = xs + le * MM_XS;
                         const double dt = hex8_gradients_half(xe, s_dphi + q * MM_DPHI, h, gr);
@@ -431,7 +445,6 @@ k_fused_hex8_mma(feb200_batch b, feb200_fused_plan plan, MmaSmem L, const double
                     }
                 }
                 __syncwarp();
-                const int n_el = min(MM_GROUP, TE - g * MM_GROUP);
 #pragma unroll 1
                 for (int j = 0; j < n_el; ++j) {
                     const int item0 = __shfl_sync(0xffffffffu, my0, j), cnt = __shfl_sync(0xffffffffu, my1, j) - item0;
