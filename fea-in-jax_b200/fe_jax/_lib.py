@@ -99,6 +99,7 @@ SIGNATURES = {
 
 _lib = None
 launches = 0   # number of C-ABI calls that enqueue kernels (bench.py reports it)
+launches_by_name = {}   # the same, per entry point (tests check which kernel ran)
 
 
 def load():
@@ -141,6 +142,7 @@ def call(name, *args):
     lib = load()
     rc = getattr(lib, name)(stream(), *args)
     launches += 1
+    launches_by_name[name] = launches_by_name.get(name, 0) + 1
     if rc != 0:
         msg = lib.feb200_last_error()
         raise Feb200Error(f"{name} failed ({rc}): {msg.decode() if msg else ''}")

@@ -508,3 +508,48 @@ def test_fused_hex8_assembly_matches_two_pass_and_oracle(fj, n, layout, shuffle)
     assert np.array_equal(np_(v_elim) == 1.0, dw_o == 1.0) and np.array_equal(np_(v_elim) == 0.0, dw_o == 0.0)
     # bitwise reproducible
     assert torch.equal(v_fused, _assemble_values(token, ebc, maps, ud)[0])
+
+
+@pytest.mark.parametrize("layout", ["M", "EM"])
+def test_fused_tensor_core_kernel_matches_scalar_kernel(fj, layout):
+    """feb200_assemble_fused_hex8_mma (block products as one FP64 mma product per element) against
+    feb200_assemble_fused_hex8 (3x3 blocks one by one) and the oracle, with the fused Dirichlet elimination;
+    tile plans with partial tiles (grid sizes that are not multiples of the 4 x 4 x 2 Morton cell)."""
+    from fe_jax.assembly import _assemble_values
+    n = 7
+    Vx, cells = orc.uniform_hex_grid(n, n - 2, n + 3)
+    rng = np.random.default_rng(11)
+    Vx = Vx + 0.1 / n * rng.uniform(-1, 1, size=Vx.shape)
+    cells = cells[rng.permutation(cells.shape[0])]
+    mp = material_params("elastic_isotropic", 3, {"M": (), "EM": (cells.shape[0],)}[layout], seed=5)
+    spec = [dict(cell="hexahedron", degree=1, qdeg=2, cells=cells, model="elastic_isotropic", mp=mp)]
+    ebc, maps, token, prob, _ = build_pair(fj, Vx, spec)
+    u = torch.zeros(Vx.size, dtype=torch.float64, device="cuda")
+    dofs = np.unique(rng.integers(0, Vx.size, size=Vx.size // 7))
+    mask = torch.zeros(prob.F, dtype=torch.float64, device="cuda")
+    mask[torch.tensor(dofs, device="cuda")] = 1.0
+    vals_g = torch.zeros_like(mask)
+    out = {}
+    for impl in ("mma", "v4"):
+        os.environ["FEB200_FUSED_IMPL"] = impl
+        try:
+            before = dict(_lib_launches(fj))
+            out[impl] = (_assemble_values(token, ebc, maps, u)[0].clone(),
+                         _assemble_values(token, ebc, maps, u, mask, vals_g, eliminate=True)[0].clone())
+            after = _lib_launches(fj)
+            name = "feb200_assemble_fused_hex8_mma" if impl == "mma" else "feb200_assemble_fused_hex8"
+            assert after.get(name, 0) - before.get(name, 0) == 2, "the requested kernel did not run"
+        finally:
+            os.environ.pop("FEB200_FUSED_IMPL", None)
+    d_o, r_o, c_o = prob.jacobian_wo_dirichlet(np.zeros(Vx.size))
+    dw_o = orc.apply_dirichlet_bcs_lhs(d_o, r_o, c_o, dofs)
+    for impl in ("mma", "v4"):
+        assert rel_err(out[impl][0], d_o) <= ASM_RTOL and rel_err(out[impl][1], dw_o) <= ASM_RTOL
+    assert rel_err(out["mma"][0], out["v4"][0].cpu().numpy()) <= 1e-13
+    # bit-reproducible across launches
+    assert torch.equal(out["mma"][0], _assemble_values(token, ebc, maps, u)[0])
+
+
+def _lib_launches(fj):
+    from fe_jax import _lib
+    return dict(_lib.launches_by_name)
