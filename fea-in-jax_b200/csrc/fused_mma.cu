@@ -6,27 +6,28 @@
 // scalar kernel of fused.cu (shared-memory wavefronts, profiles/r01_fused_v4_ncu_summary.txt).
 //
 // Same tile plan and same contract as feb200_assemble_fused_hex8 (fused.cu; reference path
-// fea.py:519-572 + fea.py:613-660 + sparse_matrix.py:157-184).  Per tile of <= 32 vertices:
-//   P0   prefetched plan data and coordinates -> shared memory
-//   A    warps pull groups of 4 elements from a tile-local counter: lane = (element, quadrature point)
-//        computes the gradients into a warp-private buffer laid out as DMMA fragments; then per element
-//        only the row tiles that hold vertices of this tile are multiplied (3 n-tiles x 2 k-steps each)
-//        and the rows are written to the item's staging record  stage[item][i][b*3+j]
-//   B    warp per vertex, lane = CSR block rank r: adds the <= 8 staged blocks in ascending slot order,
-//        applies K = lam S + mu S^T + mu tr(S) I, the Dirichlet elimination, and stores the panel row.
+// fea.py:519-572 + fea.py:613-660 + sparse_matrix.py:157-184).  One persistent CTA per SM, 8 warps; per tile
+// of <= 32 vertices (shared memory: 144 KB staged block rows + 53 KB fragment buffers + coordinates + tables):
+//   P0   data prefetched into registers one tile ahead (three dependency levels) -> shared memory; the
+//        (vertex, rank) -> source table is built with integer and-masks
+//   A    warps pull steps of 4 elements from a tile-local counter (the last round in steps of 2, so the
+//        round not every warp takes part in is short): lane = (element, quadrature point) computes the
+//        gradients into a warp-private buffer laid out as DMMA fragments; then per element only the row
+//        tiles that hold vertices of this tile are multiplied (1-3 row tiles x 3 n-tiles x 2 k-steps) and the
+//        rows go to the item's staging record  stage[item][i][b*3+j]
+//   B    lane = CSR block rank r, two vertices per warp at a time: adds the <= 8 staged blocks in ascending
+//        slot order (absent ones are predicated-off loads), applies K = lam S + mu S^T + mu tr(S) I and the
+//        Dirichlet elimination, stores the panel rows (streaming stores).
 // No floating-point atomics; the summation order is fixed by the plan, so results are bit-reproducible.
 // The work counter only decides which warp computes which element group, never the order of a sum.
+// Measured alternatives (profiles/r01_fused_mma_ncu_summary.txt): 10/12/16 warps with 2-element
+// steps, two CTAs per SM on 16-vertex tiles, panel stores transposed through shared memory, list-walking
+// or slot-pairing B phases -- all slower than this configuration.
 #include "common.cuh"
 #include "element_math.cuh"
 
-#ifndef FEB_MM_LEVELB_EARLY
-#define FEB_MM_LEVELB_EARLY 0
-#endif
 #ifndef FEB_MM_LEVELC_AFTER
 #define FEB_MM_LEVELC_AFTER 1        /* B phase: issue the coordinate prefetch after this many vertices of the warp */
-#endif
-#ifndef FEB_MM_ZEROREAD
-#define FEB_MM_ZEROREAD 0
 #endif
 #ifndef FEB_MM_WARPS
 #define FEB_MM_WARPS 8
@@ -63,7 +64,7 @@ constexpr int MM_PN = (MM_MAXDEG * 32 + MM_THREADS - 1) / MM_THREADS;
 
 struct MmaSmem {
     int tn_cap, te_cap;
-    size_t off_stage, off_zero, off_gw, off_xs, off_dphi, off_tbl, off_p0, off_itw, off_meta, off_e0, off_e1, off_itof, off_flg,
+    size_t off_stage, off_gw, off_xs, off_dphi, off_tbl, off_p0, off_itw, off_meta, off_e0, off_e1, off_itof, off_flg,
         off_ctr, total;
 };
 static inline MmaSmem mma_layout(int tn_cap, int te_cap) {
@@ -72,7 +73,6 @@ static inline MmaSmem mma_layout(int tn_cap, int te_cap) {
     L.te_cap = te_cap;
     size_t o = 0;
     L.off_stage = o; o += (size_t)tn_cap * MM_MAXVAL * MM_IS * 8;
-    L.off_zero = o;  o += 56 * 8;                                         // all-zero block read in place of absent contributions
     L.off_gw = o;    o += (size_t)MM_WARPS * MM_GROUP * MM_EL * 8;
     L.off_xs = o;    o += (size_t)te_cap * MM_XS * 8;
     L.off_dphi = o;  o += (size_t)(8 * MM_DPHI + 8) * 8;                  // basis table + quadrature weights
@@ -239,7 +239,6 @@ k_fused_hex8_mma(feb200_batch b, feb200_fused_plan plan, MmaSmem L, const double
                  const uint8_t* __restrict__ vflags, double* __restrict__ values) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* stage = reinterpret_cast<double*>(smem_raw + L.off_stage);       // [item] IS : [i][b*3+j]
-    double* zero_s = reinterpret_cast<double*>(smem_raw + L.off_zero);
     double* gw = reinterpret_cast<double*>(smem_raw + L.off_gw);             // [warp][4] EL : [ks] KS : [row][4 points], weights at 96
     double* xs = reinterpret_cast<double*>(smem_raw + L.off_xs);             // [le] XS
     double* s_dphi = reinterpret_cast<double*>(smem_raw + L.off_dphi);       // [q] DPHI : [n][3]
@@ -258,7 +257,6 @@ k_fused_hex8_mma(feb200_batch b, feb200_fused_plan plan, MmaSmem L, const double
     const int gid = lane >> 2, tig = lane & 3;
     for (int i = tid; i < 8 * 24; i += MM_THREADS) s_dphi[(i / 24) * MM_DPHI + (i % 24)] = b.dphi[i];
     if (tid < 8) s_w[tid] = b.W[tid];
-    if (tid < 56) zero_s[tid] = 0.0;
     for (int i = tid; i < L.tn_cap * MM_MAXDEG; i += MM_THREADS) tbl[i] = 0xffffffffu;
     double u_lam = 0.0, u_mu = 0.0;
     if (UNIFORM) isotropic_lame<3>(b.mp, u_lam, u_mu);
@@ -406,7 +404,6 @@ k_fused_hex8_mma(feb200_batch b, feb200_fused_plan plan, MmaSmem L, const double
 #endif
             const int rest = TE - 4 * n4 > 0 ? TE - 4 * n4 : 0;
             const int n_groups = n4 + (rest + 1) / 2;
-            bool fetched_b = false;
             int g_next = 0;
             if (lane == 0) g_next = atomicAdd(ctr, 1);
             for (;;) {
@@ -463,11 +460,8 @@ k_fused_hex8_mma(feb200_batch b, feb200_fused_plan plan, MmaSmem L, const double
                     else element_rows<1>(Ge, Bf, w0, w1, itw_e, cnt, stage_e, gid, tig);
                 }
                 __syncwarp();                                // fragment buffer free for the next group
-#if FEB_MM_LEVELB_EARLY
-                if (has_next && !fetched_b) { level_b(nxt); fetched_b = true; }
-#endif
             }
-            if (has_next && !fetched_b) level_b(nxt);
+            if (has_next) level_b(nxt);                      // after the last group: issued earlier, these loads hold scoreboards the group loop needs
         }
         __syncthreads();                                     // all block rows staged
         // ---- B: lane = CSR block rank; a warp works on MM_BV vertices at a time (independent instruction streams:
@@ -505,13 +499,8 @@ k_fused_hex8_mma(feb200_batch b, feb200_fused_plan plan, MmaSmem L, const double
                     const unsigned int bsel = (src[v] >> (4 * k)) & 0xfu;
                     const int t = (int)(((k < 4 ? tk[v].x : tk[v].y) >> (8 * (k & 3))) & 0xffu);
                     const bool on = (bsel != 0xfu) && (av[v] >= 0);
-#if FEB_MM_ZEROREAD
-                    const double* sp = on ? stage + (size_t)t * MM_IS + bsel * 3 : zero_s;
-#define MM_LD(x) (x)
-#else
                     const double* sp = stage + (size_t)t * MM_IS + bsel * 3;       // absent contributions: predicated-off loads
 #define MM_LD(x) (on ? (x) : 0.0)
-#endif
                     if (UNIFORM) {
 #pragma unroll
                         for (int i = 0; i < 3; ++i)
@@ -528,6 +517,7 @@ k_fused_hex8_mma(feb200_batch b, feb200_fused_plan plan, MmaSmem L, const double
                                 accl[UNIFORM ? 0 : v][i * 3 + j] += rho * val;
                             }
                     }
+#undef MM_LD
                 }
             }
 #pragma unroll
