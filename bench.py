@@ -43,7 +43,8 @@ def parse():
     ap.add_argument("--impl", default="feb200", choices=["feb200", "reference"])
     ap.add_argument("--cg-iters", type=int, default=100)
     ap.add_argument("--cpu-n", type=int, default=20, help="grid size of the bounded CPU-baseline sample")
-    ap.add_argument("--layout", default="M", choices=["M", "EM", "EQM"])
+    ap.add_argument("--layout", default="EQM", choices=["M", "EM", "EQM"],
+                    help="material layout: EQM = per-point Young's modulus (SURVEY 8d primary input), M = batch constant")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--two-pass", action="store_true", help="also time the generic two-pass assembly kernels")
     return ap.parse_args()
@@ -117,11 +118,11 @@ def make_problem(n_x, n, layout, x0=0.0, x1=1.0):
     return Vx, cells, mp
 
 
-def cpu_reference_sample(n, steps=1, warmup=0):
+def cpu_reference_sample(n, steps=1, warmup=0, layout="EQM"):
     """The oracle's reference-style assembly (element residual + K_e by 24 residual evaluations + COO triples +
     lexsort + duplicate sum, fea.py:613-660) on an n^3 hex8 grid; returns elements/s."""
     from oracle import fe_oracle as orc
-    Vx, cells, u, mp, bcs, vals = orc.synthetic_hex_problem(n, material_layout="M")
+    Vx, cells, u, mp, bcs, vals = orc.synthetic_hex_problem(n, material_layout=layout)
     xi, W = orc.get_quadrature("hexahedron", 2)
     _, dphi = orc.eval_basis_and_derivatives("hexahedron", 1, xi)
     prob = orc.Problem(Vx, [orc.Batch(cells, "linear", "elastic_isotropic", mp, dphi, W)])
@@ -143,16 +144,16 @@ def _cpu_worker(a):
     return cpu_reference_sample(*a)
 
 
-def cpu_reference_parallel(n, steps=1, warmup=0, procs=None):
+def cpu_reference_parallel(n, steps=1, warmup=0, procs=None, layout="EQM"):
     """The same sample on every host core at once (independent copies, one process per core): aggregate
     elements/s of the CPU restatement with all the host threads it can use."""
     import multiprocessing as mp
     procs = procs or max(1, min(os.cpu_count() or 1, 64))
     if procs == 1:
-        eps, sec, E = cpu_reference_sample(n, steps, warmup)
+        eps, sec, E = cpu_reference_sample(n, steps, warmup, layout)
         return eps, sec, E, 1
     with mp.get_context("spawn").Pool(procs) as pool:
-        out = pool.map(_cpu_worker, [(n, steps, warmup)] * procs)
+        out = pool.map(_cpu_worker, [(n, steps, warmup, layout)] * procs)
     return sum(o[0] for o in out), float(np.mean([o[1] for o in out])), out[0][2], procs
 
 
@@ -160,12 +161,13 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    eps, sec, E, cores = cpu_reference_parallel(args.cpu_n, steps=max(1, args.steps), warmup=min(1, args.warmup))
+    eps, sec, E, cores = cpu_reference_parallel(args.cpu_n, steps=max(1, args.steps), warmup=min(1, args.warmup),
+                                                layout=args.layout)
     line = {"impl": "reference", "metric": METRIC, "value": eps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"hex8 linear elasticity, uniform grid, residual+Jacobian assembly (BASELINE configs[1]); "
-                                   f"CPU sample {args.cpu_n}^3 elements of the same workload"},
+            "config": {"workload": f"hex8 linear elasticity, uniform grid, residual+Jacobian assembly (BASELINE configs[1]), "
+                                   f"material layout ({args.layout}); CPU sample {args.cpu_n}^3 elements of the same workload"},
             "cpu_baseline": {"value": eps, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"oracle (NumPy restatement of the reference algorithm: per-element K_e + COO lexsort + "
                                        f"duplicate sum) on a {args.cpu_n}^3 hex8 grid ({E} elements) run concurrently on "
@@ -309,8 +311,8 @@ def main():
         "scatter_sum": lambda: _lib.call("feb200_scatter_sum", _lib.ptr(row), _lib.ptr(col), V, 3, _lib.ptr(R_e),
                                          _lib.ptr(Rtmp), 0, _lib.ptr(mask), _lib.ptr(values), _lib.ptr(u)),
     }
-    use_mma = (fused is not None and bstruct.layout != _lib.LAYOUT_EQM
-               and os.environ.get("FEB200_FUSED_IMPL", "mma") == "mma")
+    from fe_jax.assembly import _use_tensor_core_kernel
+    use_mma = fused is not None and _use_tensor_core_kernel(ebc, 0, bstruct, fused)
     if use_mma:
         kernels["assemble_fused_hex8"] = lambda: _lib.call(
             "feb200_assemble_fused_hex8_mma", bstruct, fused.struct, _lib.ptr(ebc._vertices), _lib.ptr(plan.slot_rank[0]),
@@ -453,7 +455,7 @@ def main():
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:
-            eps, sec, Ec, cores = cpu_reference_parallel(args.cpu_n)
+            eps, sec, Ec, cores = cpu_reference_parallel(args.cpu_n, layout=args.layout)
             line["cpu_baseline"] = {"value": eps, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"oracle reference-style assembly on a {args.cpu_n}^3 hex8 grid ({Ec} elements, "
                                               f"{sec:.1f} s) on {cores} host cores concurrently (aggregate)"}

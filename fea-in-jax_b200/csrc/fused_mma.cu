@@ -64,10 +64,10 @@ constexpr int MM_PN = (MM_MAXDEG * 32 + MM_THREADS - 1) / MM_THREADS;
 
 struct MmaSmem {
     int tn_cap, te_cap;
-    size_t off_stage, off_gw, off_xs, off_dphi, off_tbl, off_p0, off_itw, off_meta, off_e0, off_e1, off_itof, off_flg,
+    size_t off_stage, off_gw, off_xs, off_eq, off_dphi, off_tbl, off_p0, off_itw, off_meta, off_e0, off_e1, off_itof, off_flg,
         off_ctr, total;
 };
-static inline MmaSmem mma_layout(int tn_cap, int te_cap) {
+static inline MmaSmem mma_layout(int tn_cap, int te_cap, bool perq) {
     MmaSmem L;
     L.tn_cap = tn_cap;
     L.te_cap = te_cap;
@@ -75,6 +75,7 @@ static inline MmaSmem mma_layout(int tn_cap, int te_cap) {
     L.off_stage = o; o += (size_t)tn_cap * MM_MAXVAL * MM_IS * 8;
     L.off_gw = o;    o += (size_t)MM_WARPS * MM_GROUP * MM_EL * 8;
     L.off_xs = o;    o += (size_t)te_cap * MM_XS * 8;
+    L.off_eq = o;    o += perq ? (size_t)te_cap * 8 * 8 : 0;              // [le][q] Young's modulus per point (layout (E,Q,M))
     L.off_dphi = o;  o += (size_t)(8 * MM_DPHI + 8) * 8;                  // basis table + quadrature weights
     L.off_p0 = o;    o += (size_t)tn_cap * 8;
     L.off_tbl = o;   o += (size_t)tn_cap * MM_MAXDEG * 4;                 // [a][r] nibble k = local node b or 0xf
@@ -110,6 +111,7 @@ struct MmaPrefetch {
     int32_t item_el;         // B
     uint32_t rowflag;        // B
     double mp[2];            // B   (E, nu) of element tid, layouts with per-element material
+    double eq[MM_PF];        // B   per-point layout: E of point (tid + j*THREADS) & 7 of element el[j]
     double x[MM_PF][3];      // C
     uint32_t flgb[MM_PN];    // C
     uint4 rk8;               // C
@@ -232,7 +234,9 @@ __device__ __forceinline__ void element_rows(const double* __restrict__ Ge, cons
         }
 }
 
-template <bool ELIM, bool UNIFORM>
+// PERQ (material layout (E,Q,M) whose Poisson ratio is constant within each element -- the host checks): mu_q = E_q / (2 (1 + nu))
+// goes into the quadrature weight and lambda / mu stays one number per element, so one product per element still suffices.
+template <bool ELIM, bool UNIFORM, bool PERQ>
 __global__ void __launch_bounds__(MM_THREADS, FEB_MM_MINBLOCKS)
 k_fused_hex8_mma(feb200_batch b, feb200_fused_plan plan, MmaSmem L, const double* __restrict__ x_vd,
                  const uint16_t* __restrict__ slot_rank, const int32_t* __restrict__ nindices,
@@ -241,6 +245,7 @@ k_fused_hex8_mma(feb200_batch b, feb200_fused_plan plan, MmaSmem L, const double
     double* stage = reinterpret_cast<double*>(smem_raw + L.off_stage);       // [item] IS : [i][b*3+j]
     double* gw = reinterpret_cast<double*>(smem_raw + L.off_gw);             // [warp][4] EL : [ks] KS : [row][4 points], weights at 96
     double* xs = reinterpret_cast<double*>(smem_raw + L.off_xs);             // [le] XS
+    double* eq_s = reinterpret_cast<double*>(smem_raw + L.off_eq);           // [le][q]  (PERQ)
     double* s_dphi = reinterpret_cast<double*>(smem_raw + L.off_dphi);       // [q] DPHI : [n][3]
     double* s_w = s_dphi + 8 * MM_DPHI;                                      // [q]
     int64_t* p0_s = reinterpret_cast<int64_t*>(smem_raw + L.off_p0);
@@ -308,6 +313,11 @@ k_fused_hex8_mma(feb200_batch b, feb200_fused_plan plan, MmaSmem L, const double
 #pragma unroll
         for (int j = 0; j < MM_PF; ++j)
             pf.vtx[j] = (pf.el[j] >= 0) ? b.conn[(int64_t)pf.el[j] * 8 + ((tid + j * MM_THREADS) & 7)] : -1;
+        if (PERQ) {
+#pragma unroll
+            for (int j = 0; j < MM_PF; ++j)
+                if (pf.el[j] >= 0) pf.eq[j] = b.mp[((int64_t)pf.el[j] * 8 + ((tid + j * MM_THREADS) & 7)) * b.M];
+        }
 #pragma unroll
         for (int j = 0; j < MM_PN; ++j) {
             const int r = (tid + j * MM_THREADS) % MM_MAXDEG;
@@ -358,12 +368,13 @@ k_fused_hex8_mma(feb200_batch b, feb200_fused_plan plan, MmaSmem L, const double
                 const int le = i >> 3, n = i & 7;
 #pragma unroll
                 for (int d = 0; d < 3; ++d) xs[le * MM_XS + n * 3 + d] = pf.x[j][d];
+                if (PERQ) eq_s[i] = pf.eq[j];
             }
         }
         if (!UNIFORM && tid < TE) {
             double lam, mu;
             isotropic_lame<3>(pf.mp, lam, mu);
-            xs[tid * MM_XS + 24] = mu;
+            xs[tid * MM_XS + 24] = PERQ ? 0.5 / (1.0 + pf.mp[1]) : mu;      // PERQ: mu_q = E_q * this
             xs[tid * MM_XS + 25] = lam / mu;
         }
         if (tid < TN) { meta_s[tid] = pf.meta | (int32_t)(pf.rowflag << 16); p0_s[tid] = pf.p0; }
@@ -427,7 +438,7 @@ k_fused_hex8_mma(feb200_batch b, feb200_fused_plan plan, MmaSmem L, const double
                         double* dst = Gw + j * MM_EL + (q >> 2) * MM_KS + (q & 3);
 #pragma unroll
                         for (int r = 0; r < 24; ++r) dst[r * 4] = gr[r];
-                        dst[96] = UNIFORM ? dt * s_w[q] : dt * s_w[q] * xe[24];
+                        dst[96] = UNIFORM ? dt * s_w[q] : (PERQ ? dt * s_w[q] * xe[24] * eq_s[le * 8 + q] : dt * s_w[q] * xe[24]);
                     }
                 } else {               // lane = (element j, point q, node half h)
                     const int j = lane >> 4, q = (lane >> 1) & 7, h = lane & 1, le = le0 + j;
@@ -438,7 +449,7 @@ k_fused_hex8_mma(feb200_batch b, feb200_fused_plan plan, MmaSmem L, const double
                         double* dst = Gw + j * MM_EL + (q >> 2) * MM_KS + (q & 3);
 #pragma unroll
                         for (int r = 0; r < 12; ++r) dst[(12 * h + r) * 4] = gr[r];
-                        if (h == 0) dst[96] = UNIFORM ? dt * s_w[q] : dt * s_w[q] * xe[24];
+                        if (h == 0) dst[96] = UNIFORM ? dt * s_w[q] : (PERQ ? dt * s_w[q] * xe[24] * eq_s[le * 8 + q] : dt * s_w[q] * xe[24]);
                     }
                 }
                 __syncwarp();
@@ -577,7 +588,9 @@ using namespace feb;
 
 extern "C" {
 
-size_t feb200_fused_mma_smem_bytes(int32_t tn_cap, int32_t te_cap) { return mma_layout(tn_cap, te_cap).total; }
+size_t feb200_fused_mma_smem_bytes(int32_t tn_cap, int32_t te_cap, int32_t material_layout) {
+    return mma_layout(tn_cap, te_cap, material_layout == FEB200_LAYOUT_EQM).total;
+}
 
 int feb200_assemble_fused_hex8_mma(feb200_stream s, const feb200_batch* bp, const feb200_fused_plan* plan, const double* x_vd,
                                    const uint16_t* slot_rank, const int32_t* nindices, const uint8_t* vertex_flags,
@@ -586,8 +599,8 @@ int feb200_assemble_fused_hex8_mma(feb200_stream s, const feb200_batch* bp, cons
     const feb200_batch& b = *bp;
     FEB_REQUIRE(b.N == 8 && b.Q == 8 && b.D == 3, FEB200_ERR_UNSUPPORTED,
                 "assemble_fused_hex8_mma: needs hex8 with 8 quadrature points");
-    FEB_REQUIRE(b.kind == FEB200_KIND_LINEAR && b.material == FEB200_MAT_ISOTROPIC && b.layout != FEB200_LAYOUT_EQM,
-                FEB200_ERR_UNSUPPORTED, "assemble_fused_hex8_mma: needs the linear isotropic material, constant per element");
+    FEB_REQUIRE(b.kind == FEB200_KIND_LINEAR && b.material == FEB200_MAT_ISOTROPIC, FEB200_ERR_UNSUPPORTED,
+                "assemble_fused_hex8_mma: needs the linear isotropic material");
     FEB_REQUIRE(b.conn && b.dphi && b.W && b.mp && b.M >= 2, FEB200_ERR_INVALID, "assemble_fused_hex8_mma: bad batch");
     FEB_REQUIRE(plan->tile_node_ptr && plan->tile_nodes && plan->tile_elem_ptr && plan->tile_elems && plan->tile_item_ptr &&
                     plan->tile_items && plan->tile_node_p0 && plan->tile_node_meta && plan->n_tiles >= 0,
@@ -596,7 +609,8 @@ int feb200_assemble_fused_hex8_mma(feb200_stream s, const feb200_batch* bp, cons
                     plan->tn_cap * MM_MAXVAL <= MM_THREADS,
                 FEB200_ERR_INVALID, "assemble_fused_hex8_mma: plan capacities tn=%d te=%d out of range", plan->tn_cap, plan->te_cap);
     if (plan->n_tiles == 0) return FEB200_OK;
-    const MmaSmem L = mma_layout(plan->tn_cap, plan->te_cap);
+    const bool perq = (b.layout == FEB200_LAYOUT_EQM);
+    const MmaSmem L = mma_layout(plan->tn_cap, plan->te_cap, perq);
     FEB_REQUIRE(L.total <= 227 * 1024, FEB200_ERR_CAPACITY, "assemble_fused_hex8_mma: tile needs %zu bytes of shared memory", L.total);
     cudaStream_t st = as_stream(s);
     const int max_grid = sm_count() * (L.total <= 113 * 1024 ? FEB_MM_MINBLOCKS : 1);
@@ -604,9 +618,15 @@ int feb200_assemble_fused_hex8_mma(feb200_stream s, const feb200_batch* bp, cons
     const bool uniform = (b.layout == FEB200_LAYOUT_M);
 #define FEB_MMA_LAUNCH(EL, UN)                                                                                         \
     {                                                                                                                  \
-        auto kern = k_fused_hex8_mma<EL, UN>;                                                                          \
-        FEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));               \
-        kern<<<grid, MM_THREADS, L.total, st>>>(b, *plan, L, x_vd, slot_rank, nindices, vertex_flags, values);         \
+        if (perq) {                                                                                                    \
+            auto kern = k_fused_hex8_mma<EL, false, true>;                                                             \
+            FEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));           \
+            kern<<<grid, MM_THREADS, L.total, st>>>(b, *plan, L, x_vd, slot_rank, nindices, vertex_flags, values);     \
+        } else {                                                                                                       \
+            auto kern = k_fused_hex8_mma<EL, UN, false>;                                                               \
+            FEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));           \
+            kern<<<grid, MM_THREADS, L.total, st>>>(b, *plan, L, x_vd, slot_rank, nindices, vertex_flags, values);     \
+        }                                                                                                              \
     }
     if (vertex_flags) {
         if (uniform) FEB_MMA_LAUNCH(true, true) else FEB_MMA_LAUNCH(true, false)

@@ -77,7 +77,7 @@ SIGNATURES = {
     "feb200_assemble_csr": (c_int32, [_P, POINTER(BatchMap), _I64, _I32, _P, _P, _P, _I32, _P, _I32, _P, _P]),
     "feb200_fused_smem_bytes": (_SZ, [_I32, _I32]),
     "feb200_assemble_fused_hex8": (c_int32, [_P, POINTER(Batch), POINTER(FusedPlan), _P, _P, _P, _P, _P, _P, _P]),
-    "feb200_fused_mma_smem_bytes": (_SZ, [_I32, _I32]),
+    "feb200_fused_mma_smem_bytes": (_SZ, [_I32, _I32, _I32]),
     "feb200_assemble_fused_hex8_mma": (c_int32, [_P, POINTER(Batch), POINTER(FusedPlan), _P, _P, _P, _P, _P]),
     "feb200_dirichlet_lhs": (c_int32, [_P, _I64, _I32, _P, _P, _P, _P]),
     "feb200_dirichlet_lhs_coo": (c_int32, [_P, _I64, _P, _P, _P, _P, _P]),

@@ -382,7 +382,7 @@ def _assemble_values(element_residual_func, ebc, assembly_map_b, u, mask=None, v
         if (b.kind == _lib.KIND_LINEAR and b.material == _lib.MAT_ISOTROPIC and plan.fused_plan(ebc, i) is not None):
             fp = plan.fused_plan(ebc, i)
             flags = _vertex_flags(ebc, mask) if (eliminate and mask is not None) else None
-            if b.layout != _lib.LAYOUT_EQM and os.environ.get("FEB200_FUSED_IMPL", "mma") == "mma":
+            if _use_tensor_core_kernel(ebc, i, b, fp):
                 _lib.call("feb200_assemble_fused_hex8_mma", b, fp.struct, _lib.ptr(ebc._vertices),
                           _lib.ptr(plan.slot_rank[i]), _lib.ptr(pat.nindices), _lib.ptr(flags), _lib.ptr(vals))
                 continue
@@ -399,6 +399,26 @@ def _assemble_values(element_residual_func, ebc, assembly_map_b, u, mask=None, v
                   _lib.ptr(pat.nindptr), pat.max_deg, _lib.ptr(vals), 1 if i > 0 else 0,
                   _lib.ptr(pat.nindices) if elim else None, _lib.ptr(mask) if elim else None)
     return vals, pat
+
+
+def _use_tensor_core_kernel(ebc, i, b, fp) -> bool:
+    """feb200_assemble_fused_hex8_mma handles materials constant per batch or per element, and per-point fields whose
+    Poisson ratio is constant within every element (one check per material array, cached on the collection);
+    anything else, or FEB200_FUSED_IMPL=v4, goes to the scalar fused kernel."""
+    if os.environ.get("FEB200_FUSED_IMPL", "mma") != "mma":
+        return False
+    if b.layout != _lib.LAYOUT_EQM:
+        return True
+    if fp.stats.get("smem_bytes_mma_per_point", 1 << 30) > 227 * 1024:
+        return False
+    cache = ebc.__dict__.setdefault("_nu_const", {})
+    mp = ebc.get_material_params(i)
+    key = (i, mp.data_ptr(), mp._version)
+    if key not in cache:
+        cache.clear()
+        nu = mp[..., 1]
+        cache[key] = bool((nu.max(dim=1).values == nu.min(dim=1).values).all().item())
+    return cache[key]
 
 
 def _vertex_flags(ebc, mask):

@@ -111,7 +111,7 @@ def _build(vertices: torch.Tensor, conn32: torch.Tensor, row_ind: torch.Tensor, 
     le = inverse - tile_elem_ptr[tile].to(torch.int64)
     # both kernels that consume the plan must fit: fused.cu (per-point material) and fused_mma.cu (the default)
     if te_cap > 96 or max(int(lib.feb200_fused_smem_bytes(tn_cap, te_cap)),
-                          int(lib.feb200_fused_mma_smem_bytes(tn_cap, te_cap))) > SMEM_LIMIT:
+                          int(lib.feb200_fused_mma_smem_bytes(tn_cap, te_cap, _lib.LAYOUT_EM))) > SMEM_LIMIT:
         return None
     packed = (le | (n_a << 12) | (a_loc_of_node[node_of_entry] << 16) | (k_of_entry << 24))
     perm = torch.argsort(inverse * N + n_a, stable=True)           # tile-major, then element, then local node
@@ -133,5 +133,6 @@ def _build(vertices: torch.Tensor, conn32: torch.Tensor, row_ind: torch.Tensor, 
     stats = dict(n_tiles=n_tiles, te_cap=te_cap, mean_nodes_per_tile=V / n_tiles,
                  element_visits_per_element=float(tile_elems.shape[0]) / E,
                  smem_bytes=int(lib.feb200_fused_smem_bytes(tn_cap, te_cap)),
-                 smem_bytes_mma=int(lib.feb200_fused_mma_smem_bytes(tn_cap, te_cap)))
+                 smem_bytes_mma=int(lib.feb200_fused_mma_smem_bytes(tn_cap, te_cap, _lib.LAYOUT_EM)),
+                 smem_bytes_mma_per_point=int(lib.feb200_fused_mma_smem_bytes(tn_cap, te_cap, _lib.LAYOUT_EQM)))
     return FusedPlan(struct, keep, n_tiles, tn_cap, te_cap, stats)

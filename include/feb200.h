@@ -176,9 +176,10 @@ int feb200_assemble_fused_hex8(feb200_stream s, const feb200_batch* b, const feb
                                const uint64_t* row_ind, const uint16_t* slot_rank, const int64_t* nindptr,
                                const int32_t* nindices, const uint8_t* vertex_flags, double* values);
 /* The same contract (same plan, same outputs) with the block products of an element evaluated as one 24 x 24 x 8
- * FP64 tensor-core product (mma.sync m8n8k4) instead of 3x3 blocks one by one; material layouts (M,) and (E,M).
- * The per-point layout (E,Q,M) stays on feb200_assemble_fused_hex8. */
-size_t feb200_fused_mma_smem_bytes(int32_t tn_cap, int32_t te_cap);
+ * FP64 tensor-core product (mma.sync m8n8k4) instead of 3x3 blocks one by one; material layouts (M,) and (E,M), and
+ * the per-point layout (E,Q,M) when the Poisson ratio is constant within each element (the caller checks; fields
+ * whose Poisson ratio varies inside an element go to feb200_assemble_fused_hex8). */
+size_t feb200_fused_mma_smem_bytes(int32_t tn_cap, int32_t te_cap, int32_t material_layout);
 int feb200_assemble_fused_hex8_mma(feb200_stream s, const feb200_batch* b, const feb200_fused_plan* plan, const double* x_vd,
                                    const uint16_t* slot_rank, const int32_t* nindices, const uint8_t* vertex_flags,
                                    double* values);
