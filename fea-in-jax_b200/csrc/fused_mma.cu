@@ -54,7 +54,10 @@ constexpr int MM_MAXVAL = 8;             // incident slots per vertex
 constexpr int MM_MAXDEG = 32;            // CSR blocks per vertex row (lane each)
 constexpr int MM_GROUP = FEB_MM_GROUP;     // elements per warp step
 constexpr int MM_KS = 104;               // doubles per k-step half of an element's fragment buffer: [row 0..23][4 points] + 8 (weights)
-constexpr int MM_EL = 212;               // doubles per element in the fragment buffer (2 * KS + 4): KS = 8, EL = 4 (mod 16) keeps the
+#ifndef FEB_MM_EL
+#define FEB_MM_EL 212
+#endif
+constexpr int MM_EL = FEB_MM_EL;               // doubles per element in the fragment buffer (2 * KS + 4): KS = 8, EL = 4 (mod 16) keeps the
                                          // geometry writes (lane = element, point) on distinct banks
 constexpr int MM_IS = 72;                // doubles per staged item: [i][b*3+j]
 constexpr int MM_XS = 26;                // doubles per element coordinate record: [n][3], mu, lambda/mu

@@ -1,4 +1,4 @@
-"""Small driver used for ncu captures of the fused assembly kernel: python profiles/profile_fused.py [n]"""
+"""Small driver used for ncu captures of the fused assembly kernel: python profiles/profile_fused.py [n] [M|EM|EQM]"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "fea-in-jax_b200")]
@@ -9,7 +9,8 @@ from fe_jax.assembly import _assemble_values, _plan
 from bench import make_problem
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-Vx, cells, mp = make_problem(n, n, "M")
+layout = sys.argv[2] if len(sys.argv) > 2 else "M"
+Vx, cells, mp = make_problem(n, n, layout)
 fe = fj.FiniteElementType(fj.CellType.hexahedron, fj.ElementFamily.P, 1, fj.LagrangeVariant.equispaced, fj.QuadratureType.default, 2)
 batch = fj.ElementBatch(fe_type=fe, n_dofs_per_basis=3, connectivity_en=cells, constitutive_model=fj.elastic_isotropic, material_params=mp)
 ebc = fj.batch_to_collection(Vx, [batch]); maps = [fj.mesh_to_sparse_assembly_map(Vx.shape[0], cells)]
