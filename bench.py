@@ -311,12 +311,12 @@ def main():
         "scatter_sum": lambda: _lib.call("feb200_scatter_sum", _lib.ptr(row), _lib.ptr(col), V, 3, _lib.ptr(R_e),
                                          _lib.ptr(Rtmp), 0, _lib.ptr(mask), _lib.ptr(values), _lib.ptr(u)),
     }
-    from fe_jax.assembly import _use_tensor_core_kernel
+    from fe_jax.assembly import _use_tensor_core_kernel, _material_hints
     use_mma = fused is not None and _use_tensor_core_kernel(ebc, 0, bstruct, fused)
     if use_mma:
         kernels["assemble_fused_hex8"] = lambda: _lib.call(
             "feb200_assemble_fused_hex8_mma", bstruct, fused.struct, _lib.ptr(ebc._vertices), _lib.ptr(plan.slot_rank[0]),
-            _lib.ptr(pat.nindices), _lib.ptr(vflags), _lib.ptr(J_vals))
+            _lib.ptr(pat.nindices), _lib.ptr(vflags), _material_hints(ebc, 0, bstruct), _lib.ptr(J_vals))
     elif fused is not None:
         kernels["assemble_fused_hex8"] = lambda: _lib.call(
             "feb200_assemble_fused_hex8", bstruct, fused.struct, _lib.ptr(ebc._vertices), _lib.ptr(row),

@@ -237,9 +237,14 @@ __device__ __forceinline__ void element_rows(const double* __restrict__ Ge, cons
         }
 }
 
-// PERQ (material layout (E,Q,M) whose Poisson ratio is constant within each element -- the host checks): mu_q = E_q / (2 (1 + nu))
-// goes into the quadrature weight and lambda / mu stays one number per element, so one product per element still suffices.
-template <bool ELIM, bool UNIFORM, bool PERQ>
+// WM, how the material enters the quadrature weight of the product:
+//   0  not at all: one (lambda, mu) for the batch, applied in phase B                          layout (M,)
+//   1  w_q * mu_e                                                                               layout (E,M)
+//   2  w_q * E_q / (2 (1 + nu_e)): per-point Young's modulus, Poisson ratio per element        layout (E,Q,M), checked by the host
+// For WM > 0 phase B needs rho = lambda / mu = 2 nu / (1 - 2 nu): K = sum rho_k S'_k + (sum S'_k)^T + tr(sum S'_k) I.
+// UNIFORM: rho is one number for the batch (WM = 0, or the caller's hint that every element has the same Poisson
+// ratio), so the blocks are summed first and combined once; otherwise rho is applied per contribution.
+template <bool ELIM, bool UNIFORM, int WM>
 __global__ void __launch_bounds__(MM_THREADS, FEB_MM_MINBLOCKS)
 k_fused_hex8_mma(feb200_batch b, feb200_fused_plan plan, MmaSmem L, const double* __restrict__ x_vd,
                  const uint16_t* __restrict__ slot_rank, const int32_t* __restrict__ nindices,
@@ -248,7 +253,7 @@ k_fused_hex8_mma(feb200_batch b, feb200_fused_plan plan, MmaSmem L, const double
     double* stage = reinterpret_cast<double*>(smem_raw + L.off_stage);       // [item] IS : [i][b*3+j]
     double* gw = reinterpret_cast<double*>(smem_raw + L.off_gw);             // [warp][4] EL : [ks] KS : [row][4 points], weights at 96
     double* xs = reinterpret_cast<double*>(smem_raw + L.off_xs);             // [le] XS
-    double* eq_s = reinterpret_cast<double*>(smem_raw + L.off_eq);           // [le][q]  (PERQ)
+    double* eq_s = reinterpret_cast<double*>(smem_raw + L.off_eq);           // [le][q]  (WM == 2)
     double* s_dphi = reinterpret_cast<double*>(smem_raw + L.off_dphi);       // [q] DPHI : [n][3]
     double* s_w = s_dphi + 8 * MM_DPHI;                                      // [q]
     int64_t* p0_s = reinterpret_cast<int64_t*>(smem_raw + L.off_p0);
@@ -267,7 +272,10 @@ k_fused_hex8_mma(feb200_batch b, feb200_fused_plan plan, MmaSmem L, const double
     if (tid < 8) s_w[tid] = b.W[tid];
     for (int i = tid; i < L.tn_cap * MM_MAXDEG; i += MM_THREADS) tbl[i] = 0xffffffffu;
     double u_lam = 0.0, u_mu = 0.0;
-    if (UNIFORM) isotropic_lame<3>(b.mp, u_lam, u_mu);
+    if (UNIFORM) {
+        isotropic_lame<3>(b.mp, u_lam, u_mu);
+        if (WM > 0) { u_lam = u_lam / u_mu; u_mu = 1.0; }                     // mu is already in the weights: K = rho S' + S'^T + tr(S') I
+    }
 
     struct TilePtr { int n0, n1, e0, e1, i0, i1; };
     auto load_ptr = [&](int tile) {
@@ -287,7 +295,7 @@ k_fused_hex8_mma(feb200_batch b, feb200_fused_plan plan, MmaSmem L, const double
             const int i = tid + j * MM_THREADS;
             pf.el[j] = (i < TE * 8) ? plan.tile_elems[e0 + (i >> 3)] : -1;
         }
-        pf.el_own = (!UNIFORM && tid < TE) ? plan.tile_elems[e0 + tid] : -1;
+        pf.el_own = (WM > 0 && tid < TE) ? plan.tile_elems[e0 + tid] : -1;
         pf.item = pf.item_prev = pf.item_next = 0xffffffffu;
         if (tid < NI) {
             pf.item = plan.tile_items[i0 + tid];
@@ -316,7 +324,7 @@ k_fused_hex8_mma(feb200_batch b, feb200_fused_plan plan, MmaSmem L, const double
 #pragma unroll
         for (int j = 0; j < MM_PF; ++j)
             pf.vtx[j] = (pf.el[j] >= 0) ? b.conn[(int64_t)pf.el[j] * 8 + ((tid + j * MM_THREADS) & 7)] : -1;
-        if (PERQ) {
+        if (WM == 2) {
 #pragma unroll
             for (int j = 0; j < MM_PF; ++j)
                 if (pf.el[j] >= 0) pf.eq[j] = b.mp[((int64_t)pf.el[j] * 8 + ((tid + j * MM_THREADS) & 7)) * b.M];
@@ -328,7 +336,7 @@ k_fused_hex8_mma(feb200_batch b, feb200_fused_plan plan, MmaSmem L, const double
         }
         pf.item_el = (pf.item != 0xffffffffu) ? plan.tile_elems[e0 + (pf.item & 0xfff)] : -1;
         pf.rowflag = (ELIM && pf.node >= 0) ? (uint32_t)vflags[pf.node] : 0u;
-        if (!UNIFORM && pf.el_own >= 0) {
+        if (WM > 0 && pf.el_own >= 0) {
             int qs;
             const double* mp = mp_of(b, pf.el_own, qs);
             pf.mp[0] = mp[0];
@@ -371,13 +379,13 @@ k_fused_hex8_mma(feb200_batch b, feb200_fused_plan plan, MmaSmem L, const double
                 const int le = i >> 3, n = i & 7;
 #pragma unroll
                 for (int d = 0; d < 3; ++d) xs[le * MM_XS + n * 3 + d] = pf.x[j][d];
-                if (PERQ) eq_s[i] = pf.eq[j];
+                if (WM == 2) eq_s[i] = pf.eq[j];
             }
         }
-        if (!UNIFORM && tid < TE) {
+        if (WM > 0 && tid < TE) {
             double lam, mu;
             isotropic_lame<3>(pf.mp, lam, mu);
-            xs[tid * MM_XS + 24] = PERQ ? 0.5 / (1.0 + pf.mp[1]) : mu;      // PERQ: mu_q = E_q * this
+            xs[tid * MM_XS + 24] = (WM == 2) ? 0.5 / (1.0 + pf.mp[1]) : mu;   // WM 2: mu_q = E_q * this
             xs[tid * MM_XS + 25] = lam / mu;
         }
         if (tid < TN) { meta_s[tid] = pf.meta | (int32_t)(pf.rowflag << 16); p0_s[tid] = pf.p0; }
@@ -441,7 +449,7 @@ k_fused_hex8_mma(feb200_batch b, feb200_fused_plan plan, MmaSmem L, const double
                         double* dst = Gw + j * MM_EL + (q >> 2) * MM_KS + (q & 3);
 #pragma unroll
                         for (int r = 0; r < 24; ++r) dst[r * 4] = gr[r];
-                        dst[96] = UNIFORM ? dt * s_w[q] : (PERQ ? dt * s_w[q] * xe[24] * eq_s[le * 8 + q] : dt * s_w[q] * xe[24]);
+                        dst[96] = (WM == 0) ? dt * s_w[q] : (WM == 2 ? dt * s_w[q] * xe[24] * eq_s[le * 8 + q] : dt * s_w[q] * xe[24]);
                     }
                 } else {               // lane = (element j, point q, node half h)
                     const int j = lane >> 4, q = (lane >> 1) & 7, h = lane & 1, le = le0 + j;
@@ -452,7 +460,7 @@ k_fused_hex8_mma(feb200_batch b, feb200_fused_plan plan, MmaSmem L, const double
                         double* dst = Gw + j * MM_EL + (q >> 2) * MM_KS + (q & 3);
 #pragma unroll
                         for (int r = 0; r < 12; ++r) dst[(12 * h + r) * 4] = gr[r];
-                        if (h == 0) dst[96] = UNIFORM ? dt * s_w[q] : (PERQ ? dt * s_w[q] * xe[24] * eq_s[le * 8 + q] : dt * s_w[q] * xe[24]);
+                        if (h == 0) dst[96] = (WM == 0) ? dt * s_w[q] : (WM == 2 ? dt * s_w[q] * xe[24] * eq_s[le * 8 + q] : dt * s_w[q] * xe[24]);
                     }
                 }
                 __syncwarp();
@@ -597,7 +605,7 @@ size_t feb200_fused_mma_smem_bytes(int32_t tn_cap, int32_t te_cap, int32_t mater
 
 int feb200_assemble_fused_hex8_mma(feb200_stream s, const feb200_batch* bp, const feb200_fused_plan* plan, const double* x_vd,
                                    const uint16_t* slot_rank, const int32_t* nindices, const uint8_t* vertex_flags,
-                                   double* values) {
+                                   int32_t material_hints, double* values) {
     FEB_REQUIRE(bp && plan && x_vd && slot_rank && nindices && values, FEB200_ERR_INVALID, "assemble_fused_hex8_mma: null pointer");
     const feb200_batch& b = *bp;
     FEB_REQUIRE(b.N == 8 && b.Q == 8 && b.D == 3, FEB200_ERR_UNSUPPORTED,
@@ -618,24 +626,20 @@ int feb200_assemble_fused_hex8_mma(feb200_stream s, const feb200_batch* bp, cons
     cudaStream_t st = as_stream(s);
     const int max_grid = sm_count() * (L.total <= 113 * 1024 ? FEB_MM_MINBLOCKS : 1);
     const int grid = plan->n_tiles < max_grid ? plan->n_tiles : max_grid;
-    const bool uniform = (b.layout == FEB200_LAYOUT_M);
-#define FEB_MMA_LAUNCH(EL, UN)                                                                                         \
+    const int wm = perq ? 2 : (b.layout == FEB200_LAYOUT_EM ? 1 : 0);
+    const bool uniform = (wm == 0) || (material_hints & FEB200_HINT_UNIFORM_POISSON);
+#define FEB_MMA_LAUNCH(EL, UN, WMODE)                                                                                  \
     {                                                                                                                  \
-        if (perq) {                                                                                                    \
-            auto kern = k_fused_hex8_mma<EL, false, true>;                                                             \
-            FEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));           \
-            kern<<<grid, MM_THREADS, L.total, st>>>(b, *plan, L, x_vd, slot_rank, nindices, vertex_flags, values);     \
-        } else {                                                                                                       \
-            auto kern = k_fused_hex8_mma<EL, UN, false>;                                                               \
-            FEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));           \
-            kern<<<grid, MM_THREADS, L.total, st>>>(b, *plan, L, x_vd, slot_rank, nindices, vertex_flags, values);     \
-        }                                                                                                              \
+        auto kern = k_fused_hex8_mma<EL, UN, WMODE>;                                                                   \
+        FEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));               \
+        kern<<<grid, MM_THREADS, L.total, st>>>(b, *plan, L, x_vd, slot_rank, nindices, vertex_flags, values);         \
     }
-    if (vertex_flags) {
-        if (uniform) FEB_MMA_LAUNCH(true, true) else FEB_MMA_LAUNCH(true, false)
-    } else {
-        if (uniform) FEB_MMA_LAUNCH(false, true) else FEB_MMA_LAUNCH(false, false)
-    }
+#define FEB_MMA_DISPATCH(EL)                                                                                           \
+    if (wm == 0) FEB_MMA_LAUNCH(EL, true, 0)                                                                           \
+    else if (wm == 1) { if (uniform) FEB_MMA_LAUNCH(EL, true, 1) else FEB_MMA_LAUNCH(EL, false, 1) }                   \
+    else { if (uniform) FEB_MMA_LAUNCH(EL, true, 2) else FEB_MMA_LAUNCH(EL, false, 2) }
+    if (vertex_flags) { FEB_MMA_DISPATCH(true) } else { FEB_MMA_DISPATCH(false) }
+#undef FEB_MMA_DISPATCH
 #undef FEB_MMA_LAUNCH
     FEB_CHECK_LAUNCH("assemble_fused_hex8_mma");
     return FEB200_OK;

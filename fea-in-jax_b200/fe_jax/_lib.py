@@ -18,6 +18,7 @@ FEB200_MAX_BATCHES = 16
 KIND_LINEAR, KIND_HYPER = 0, 1
 MAT_ISOTROPIC, MAT_ORTHOTROPIC, MAT_SVK, MAT_MOONEY_RIVLIN = 0, 1, 2, 3
 LAYOUT_M, LAYOUT_EM, LAYOUT_EQM = 0, 1, 2
+HINT_UNIFORM_POISSON = 1
 CG_INIT_SPMV, CG_INIT_VECTORS, CG_INIT_FINALIZE, CG_SPMV, CG_PAP, CG_UPDATE_XR, CG_UPDATE_P = range(7)
 
 
@@ -78,7 +79,7 @@ SIGNATURES = {
     "feb200_fused_smem_bytes": (_SZ, [_I32, _I32]),
     "feb200_assemble_fused_hex8": (c_int32, [_P, POINTER(Batch), POINTER(FusedPlan), _P, _P, _P, _P, _P, _P, _P]),
     "feb200_fused_mma_smem_bytes": (_SZ, [_I32, _I32, _I32]),
-    "feb200_assemble_fused_hex8_mma": (c_int32, [_P, POINTER(Batch), POINTER(FusedPlan), _P, _P, _P, _P, _P]),
+    "feb200_assemble_fused_hex8_mma": (c_int32, [_P, POINTER(Batch), POINTER(FusedPlan), _P, _P, _P, _P, _I32, _P]),
     "feb200_dirichlet_lhs": (c_int32, [_P, _I64, _I32, _P, _P, _P, _P]),
     "feb200_dirichlet_lhs_coo": (c_int32, [_P, _I64, _P, _P, _P, _P, _P]),
     "feb200_csr_diagonal": (c_int32, [_P, _I64, _I32, _P, _P, _P, _P]),

@@ -384,7 +384,8 @@ def _assemble_values(element_residual_func, ebc, assembly_map_b, u, mask=None, v
             flags = _vertex_flags(ebc, mask) if (eliminate and mask is not None) else None
             if _use_tensor_core_kernel(ebc, i, b, fp):
                 _lib.call("feb200_assemble_fused_hex8_mma", b, fp.struct, _lib.ptr(ebc._vertices),
-                          _lib.ptr(plan.slot_rank[i]), _lib.ptr(pat.nindices), _lib.ptr(flags), _lib.ptr(vals))
+                          _lib.ptr(plan.slot_rank[i]), _lib.ptr(pat.nindices), _lib.ptr(flags),
+                          _material_hints(ebc, i, b), _lib.ptr(vals))
                 continue
             _lib.call("feb200_assemble_fused_hex8", b, fp.struct, _lib.ptr(ebc._vertices), _lib.ptr(plan._keep[i][0]),
                       _lib.ptr(plan.slot_rank[i]), _lib.ptr(pat.nindptr), _lib.ptr(pat.nindices),
@@ -401,6 +402,29 @@ def _assemble_values(element_residual_func, ebc, assembly_map_b, u, mask=None, v
     return vals, pat
 
 
+def _poisson_facts(ebc, i):
+    """(constant within every element, identical everywhere) for the Poisson ratio of batch i; one reduction per
+    material array, cached on the collection and redone when the array is replaced or written to."""
+    cache = ebc.__dict__.setdefault("_nu_facts", {})
+    mp = ebc.get_material_params(i)
+    key = (i, mp.data_ptr(), mp._version)
+    if key not in cache:
+        cache.clear()
+        nu = mp[..., 1]
+        if nu.dim() == 0:
+            cache[key] = (True, True)
+        else:
+            per_el = True if nu.dim() == 1 else bool((nu.max(dim=1).values == nu.min(dim=1).values).all().item())
+            cache[key] = (per_el, bool((nu.max() == nu.min()).item()))
+    return cache[key]
+
+
+def _material_hints(ebc, i, b) -> int:
+    if b.layout == _lib.LAYOUT_M:
+        return 0
+    return _lib.HINT_UNIFORM_POISSON if _poisson_facts(ebc, i)[1] else 0
+
+
 def _use_tensor_core_kernel(ebc, i, b, fp) -> bool:
     """feb200_assemble_fused_hex8_mma handles materials constant per batch or per element, and per-point fields whose
     Poisson ratio is constant within every element (one check per material array, cached on the collection);
@@ -411,14 +435,7 @@ def _use_tensor_core_kernel(ebc, i, b, fp) -> bool:
         return True
     if fp.stats.get("smem_bytes_mma_per_point", 1 << 30) > 227 * 1024:
         return False
-    cache = ebc.__dict__.setdefault("_nu_const", {})
-    mp = ebc.get_material_params(i)
-    key = (i, mp.data_ptr(), mp._version)
-    if key not in cache:
-        cache.clear()
-        nu = mp[..., 1]
-        cache[key] = bool((nu.max(dim=1).values == nu.min(dim=1).values).all().item())
-    return cache[key]
+    return _poisson_facts(ebc, i)[0]
 
 
 def _vertex_flags(ebc, mask):

@@ -178,11 +178,15 @@ int feb200_assemble_fused_hex8(feb200_stream s, const feb200_batch* b, const feb
 /* The same contract (same plan, same outputs) with the block products of an element evaluated as one 24 x 24 x 8
  * FP64 tensor-core product (mma.sync m8n8k4) instead of 3x3 blocks one by one; material layouts (M,) and (E,M), and
  * the per-point layout (E,Q,M) when the Poisson ratio is constant within each element (the caller checks; fields
- * whose Poisson ratio varies inside an element go to feb200_assemble_fused_hex8). */
+ * whose Poisson ratio varies inside an element go to feb200_assemble_fused_hex8).
+ * material_hints: FEB200_HINT_UNIFORM_POISSON = every entry of the material array has the same Poisson ratio (heterogeneous
+ * stiffness, one Poisson ratio): lambda / mu is then one number and the blocks are combined once per CSR block instead
+ * of once per contribution.  The caller guarantees what it hints. */
+#define FEB200_HINT_UNIFORM_POISSON 1
 size_t feb200_fused_mma_smem_bytes(int32_t tn_cap, int32_t te_cap, int32_t material_layout);
 int feb200_assemble_fused_hex8_mma(feb200_stream s, const feb200_batch* b, const feb200_fused_plan* plan, const double* x_vd,
                                    const uint16_t* slot_rank, const int32_t* nindices, const uint8_t* vertex_flags,
-                                   double* values);
+                                   int32_t material_hints, double* values);
 
 /* apply_dirichlet_bcs_lhs on the node-pattern CSR (sparse_matrix.py:157-184). mask: (U*V) 0/1 doubles. */
 int feb200_dirichlet_lhs(feb200_stream s, int64_t V, int32_t U, const int64_t* nindptr, const int32_t* nindices,

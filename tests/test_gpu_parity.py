@@ -510,7 +510,7 @@ def test_fused_hex8_assembly_matches_two_pass_and_oracle(fj, n, layout, shuffle)
     assert torch.equal(v_fused, _assemble_values(token, ebc, maps, ud)[0])
 
 
-@pytest.mark.parametrize("layout", ["M", "EM", "EQM_nu_per_element", "EQM"])
+@pytest.mark.parametrize("layout", ["M", "EM", "EM_nu_uniform", "EQM_nu_per_element", "EQM_nu_uniform", "EQM"])
 def test_fused_tensor_core_kernel_matches_scalar_kernel(fj, layout):
     """feb200_assemble_fused_hex8_mma (block products as one FP64 mma product per element) against
     feb200_assemble_fused_hex8 (3x3 blocks one by one) and the oracle, with the fused Dirichlet elimination;
@@ -521,9 +521,12 @@ def test_fused_tensor_core_kernel_matches_scalar_kernel(fj, layout):
     rng = np.random.default_rng(11)
     Vx = Vx + 0.1 / n * rng.uniform(-1, 1, size=Vx.shape)
     cells = cells[rng.permutation(cells.shape[0])]
-    mp = material_params("elastic_isotropic", 3, {"M": (), "EM": (cells.shape[0],)}.get(layout, (cells.shape[0], 8)), seed=5)
+    mp = material_params("elastic_isotropic", 3, {"M": (), "EM": (cells.shape[0],), "EM_nu_uniform": (cells.shape[0],)}
+                         .get(layout, (cells.shape[0], 8)), seed=5)
     if layout == "EQM_nu_per_element":
         mp[..., 1] = mp[:, :1, 1]            # Poisson ratio constant within each element: tensor-core kernel eligible
+    if layout.endswith("nu_uniform"):
+        mp[..., 1] = 0.3                     # one Poisson ratio for the batch: FEB200_HINT_UNIFORM_POISSON path
     spec = [dict(cell="hexahedron", degree=1, qdeg=2, cells=cells, model="elastic_isotropic", mp=mp)]
     ebc, maps, token, prob, _ = build_pair(fj, Vx, spec)
     u = torch.zeros(Vx.size, dtype=torch.float64, device="cuda")
