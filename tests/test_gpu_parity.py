@@ -559,3 +559,36 @@ def test_fused_tensor_core_kernel_matches_scalar_kernel(fj, layout):
 def _lib_launches(fj):
     from fe_jax import _lib
     return dict(_lib.launches_by_name)
+
+
+@pytest.mark.parametrize("keep", [0.7, 0.35])
+def test_fused_kernels_on_grid_with_missing_elements(fj, keep):
+    """Irregular connectivity for the tile plan: a jittered hex8 grid with elements removed at random, so vertices have
+    1..8 incident elements, 8..27 neighbour blocks, some none at all, and tiles are ragged.  Tensor-core kernel, scalar
+    fused kernel and two-pass path against the oracle (values) and each other."""
+    from fe_jax.assembly import _assemble_values, _plan
+    n = 8
+    Vx, cells = orc.uniform_hex_grid(n, n - 1, n + 1)
+    rng = np.random.default_rng(int(keep * 100))
+    Vx = Vx + 0.1 / n * rng.uniform(-1, 1, size=Vx.shape)
+    cells = cells[rng.uniform(size=cells.shape[0]) < keep]
+    cells = cells[rng.permutation(cells.shape[0])]
+    mp = material_params("elastic_isotropic", 3, (cells.shape[0],), seed=9)
+    spec = [dict(cell="hexahedron", degree=1, qdeg=2, cells=cells, model="elastic_isotropic", mp=mp)]
+    u = torch.zeros(Vx.size, dtype=torch.float64, device="cuda")
+    out = {}
+    for impl in ("mma", "v4", "two-pass"):
+        os.environ["FEB200_FUSED_IMPL"] = impl if impl != "two-pass" else "mma"
+        os.environ["FEB200_FUSED"] = "0" if impl == "two-pass" else "1"
+        try:
+            ebc, maps, token, prob, _ = build_pair(fj, Vx, spec)
+            assert (_plan(ebc, maps).fused_plan(ebc, 0) is None) == (impl == "two-pass")
+            out[impl] = _assemble_values(token, ebc, maps, u)[0].clone()
+        finally:
+            os.environ.pop("FEB200_FUSED_IMPL", None)
+            os.environ["FEB200_FUSED"] = "1"
+    d_o, r_o, c_o = prob.jacobian_wo_dirichlet(np.zeros(Vx.size))
+    for impl, v in out.items():
+        assert rel_err(v, d_o) <= ASM_RTOL, impl
+    assert rel_err(out["mma"], out["two-pass"].cpu().numpy()) <= 1e-13
+    assert torch.equal(out["v4"], out["two-pass"])          # same summation order by construction
