@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--cpu-n", type=int, default=20, help="grid size of the bounded CPU-baseline sample")
     ap.add_argument("--layout", default="EQM", choices=["M", "EM", "EQM"],
                     help="material layout: EQM = per-point Young's modulus (SURVEY 8d primary input), M = batch constant")
+    ap.add_argument("--physics", default="linear", choices=["linear", "hyper"],
+                    help="hyper = BASELINE configs[2]: hyperelastic (St. Venant-Kirchhoff) residual and tangent, generic two-pass "
+                         "assembly; the CPU baseline legs stay on the linear workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--two-pass", action="store_true", help="also time the generic two-pass assembly kernels")
     return ap.parse_args()
@@ -233,8 +236,9 @@ def main():
     F = 3 * V
     fe = fj.FiniteElementType(fj.CellType.hexahedron, fj.ElementFamily.P, 1, fj.LagrangeVariant.equispaced,
                               fj.QuadratureType.default, 2)
-    batch = fj.ElementBatch(fe_type=fe, n_dofs_per_basis=3, connectivity_en=cells, constitutive_model=fj.elastic_isotropic,
-                            material_params=mp)
+    hyper = args.physics == "hyper"
+    batch = fj.ElementBatch(fe_type=fe, n_dofs_per_basis=3, connectivity_en=cells,
+                            constitutive_model=fj.st_venant_kirchhoff if hyper else fj.elastic_isotropic, material_params=mp)
     t_setup = time.perf_counter()
     ebc = fj.batch_to_collection(Vx, [batch])
     maps = [fj.mesh_to_sparse_assembly_map(V, cells)]
@@ -253,11 +257,13 @@ def main():
     for c in range(3):
         mask[3 * left + c] = 1.0
     mask[3 * right] = 1.0
-    values[3 * right] = 0.01
+    right_val = 0.0005 * world if args.physics == "hyper" else 0.01
+    values[3 * right] = right_val
     dofs = mask.nonzero().reshape(-1)
-    u_host = torch.from_numpy(1e-3 * np.random.default_rng(1).uniform(size=F)).pin_memory()
+    # hyperelastic runs keep the random state in the small-strain range (h = 1/n) so the tangent stays positive definite
+    u_host = torch.from_numpy((1e-5 if hyper else 1e-3) * np.random.default_rng(1).uniform(size=F)).pin_memory()
     u = u_host.to(dev)
-    token = fj.linear_elasticity_residual
+    token = fj.hyperelasticity_residual if hyper else fj.linear_elasticity_residual
     J_vals = torch.empty(nnz, dtype=torch.float64, device=dev)
     R_host = torch.empty(F, dtype=torch.float64).pin_memory()
     diag_host = torch.empty(F, dtype=torch.float64).pin_memory()
@@ -302,7 +308,7 @@ def main():
     Rtmp = torch.empty(F, dtype=torch.float64, device=dev)
     row = maps[0].indptr.reshape(-1).view(torch.int64)
     col = maps[0].indices.reshape(-1).view(torch.int64)
-    fused = plan.fused_plan(ebc, 0)
+    fused = None if hyper else plan.fused_plan(ebc, 0)          # the fused kernels are for the linear isotropic tangent
     from fe_jax.assembly import _vertex_flags
     vflags = _vertex_flags(ebc, mask)
     kernels = {
@@ -364,7 +370,7 @@ def main():
         lm = part.slab_local_mesh(rank, world, Vx, cells, ids[0].ravel(), ids[n].ravel())
         bc_v = np.concatenate([np.repeat(left.cpu().numpy(), 3), right.cpu().numpy()])
         bc_c = np.concatenate([np.tile(np.arange(3), left.numel()), np.zeros(right.numel(), dtype=np.int64)])
-        bc_val = np.concatenate([np.zeros(3 * left.numel()), np.full(right.numel(), 0.01)])
+        bc_val = np.concatenate([np.zeros(3 * left.numel()), np.full(right.numel(), right_val)])
         dp = part.DistributedProblem(fj, part.TorchDistComm(), [lm], lambda m: [batch],
                                      lambda m: (np.stack([bc_v, bc_c], axis=1), bc_val), [dev], token)
         rp = dp.rp[0]
@@ -438,7 +444,9 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": f"3D hex8 linear elasticity, uniform grid {n}^3 elements per GPU (BASELINE configs[1]), "
-                                   f"residual + Jacobian CSR assembly with fused Dirichlet elimination; material layout ({args.layout})",
+                                   f"residual + Jacobian CSR assembly with fused Dirichlet elimination; material layout ({args.layout})"
+                                   + ("; HYPERELASTIC (St. Venant-Kirchhoff) residual and tangent, generic two-pass assembly "
+                                      "(BASELINE configs[2])" if hyper else ""),
                        "elements_per_gpu": E, "dofs_per_gpu": F, "nnz_per_gpu": nnz, "l2_policy": "inputs larger than L2",
                        "setup_s": t_setup},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s",
