@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .containers import BCSR, COO, NodePattern
+from .containers import COO, NodePattern
 from .mesh import as_device, mesh_to_element_coords
 from .physics import resolve_model, resolve_residual
 from .tables import FiniteElementType, eval_basis_and_derivatives, get_quadrature

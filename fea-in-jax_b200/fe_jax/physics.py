@@ -11,7 +11,6 @@ call runs the batched kernel on a one-element batch.
 """
 from __future__ import annotations
 
-import numpy as np
 import torch
 
 from . import _lib

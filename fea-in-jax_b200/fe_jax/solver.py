@@ -16,7 +16,6 @@ from typing import Callable, Optional
 import torch
 
 from . import _lib
-from .containers import COO
 from .krylov import JacobiPreconditioner, cg_on_pattern
 from .mesh import as_device
 from .sparse import apply_dirichlet_bcs_lhs

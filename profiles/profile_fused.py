@@ -1,9 +1,9 @@
 """Small driver used for ncu captures of the fused assembly kernel: python profiles/profile_fused.py [n] [M|EM|EQM]"""
-import os, sys, time
+import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "fea-in-jax_b200")]
 os.environ.setdefault("FEB200_QUIET", "1")
-import numpy as np, torch
+import torch
 import fe_jax as fj
 from fe_jax.assembly import _assemble_values, _plan
 from bench import make_problem

@@ -3,7 +3,7 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "fea-in-jax_b200")]
 os.environ.setdefault("FEB200_QUIET", "1")
-import numpy as np, torch
+import torch
 import fe_jax as fj
 from fe_jax import _lib
 from fe_jax.assembly import _plan
