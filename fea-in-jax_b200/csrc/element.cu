@@ -361,10 +361,17 @@ __global__ void k_tangent_general_ct(feb200_batch b, int epb, int per_el, const 
                 }
         }
         double* out = K_e + ((e * N + a) * (int64_t)N) * D2;
+        if ((N * D2) % 2 == 0) {       // the row block of a node is N * D2 doubles: 16-byte aligned, stored as pairs
+            double2* out2 = reinterpret_cast<double2*>(out);
 #pragma unroll
-        for (int bn = 0; bn < N; ++bn)
+            for (int i = 0; i < N * D2 / 2; ++i)
+                out2[i] = make_double2(acc[(2 * i) / D2][(2 * i) % D2], acc[(2 * i + 1) / D2][(2 * i + 1) % D2]);
+        } else {
 #pragma unroll
-            for (int c = 0; c < D2; ++c) out[bn * D2 + c] = acc[bn][c];
+            for (int bn = 0; bn < N; ++bn)
+#pragma unroll
+                for (int c = 0; c < D2; ++c) out[bn * D2 + c] = acc[bn][c];
+        }
     }
 }
 
