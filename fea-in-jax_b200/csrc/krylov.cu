@@ -202,6 +202,86 @@ __global__ void k_cg_advance(double* scalars, int32_t* counters, double* hist, i
     if (!(rs > scalars[S_ATOL2] && k < counters[C_MAXITER])) counters[C_DONE] = 1;
 }
 
+// ---- batched CG: C independent systems laid side by side (block-diagonal matrix, copy c owns DoFs [c*len, (c+1)*len)) ---
+// One CTA per copy: every scalar of the iteration is a reduction over that copy's segment only, so a whole CG step
+// after the SpMV (alpha, x and r update, z, the two new dot products, beta, p update, loop test) is ONE kernel and each
+// copy keeps its own alpha / beta / iteration count / stopping test, exactly as vmap(cg) gives in the reference
+// (solve_cg.py:20-137 under tests/test_microscale_bvp.py).  Finished copies are skipped.
+// scal[c*4 + {0,1,2,3}] = gamma, rr, bb, atol2 ; cnt[c*2 + {0,1}] = k, done ; hist[c*maxiter + k]
+__global__ void __launch_bounds__(256) k_bcg_init(int64_t len, const double* __restrict__ b, const double* __restrict__ Ax,
+                                                  const double* __restrict__ inv_diag, double* __restrict__ r,
+                                                  double* __restrict__ p, double* scal, int32_t* cnt, double* hist,
+                                                  double tol, double atol, int maxiter) {
+    const int64_t c = blockIdx.x, o = c * len;
+    double d[3] = {0.0, 0.0, 0.0};
+    for (int64_t i = threadIdx.x; i < len; i += blockDim.x) {
+        const double bi = b[o + i];
+        const double ri = bi - Ax[o + i];
+        const double zi = inv_diag ? ri * inv_diag[o + i] : ri;
+        r[o + i] = ri;
+        p[o + i] = zi;
+        d[0] += ri * zi;
+        d[1] += ri * ri;
+        d[2] += bi * bi;
+    }
+    __shared__ double red[96];
+    block_sum<3>(d, red);
+    if (threadIdx.x == 0) {
+        const double atol2 = fmax(tol * tol * d[2], atol * atol);
+        scal[c * 4 + 0] = d[0];
+        scal[c * 4 + 1] = d[1];
+        scal[c * 4 + 2] = d[2];
+        scal[c * 4 + 3] = atol2;
+        if (maxiter > 0) hist[c * (int64_t)maxiter] = sqrt(d[1]);
+        const double rs = inv_diag ? d[1] : d[0];
+        cnt[c * 2 + 0] = 0;
+        cnt[c * 2 + 1] = (rs > atol2 && 0 < maxiter) ? 0 : 1;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_bcg_step(int64_t len, const double* __restrict__ Ap,
+                                                  const double* __restrict__ inv_diag, double* __restrict__ x,
+                                                  double* __restrict__ r, double* __restrict__ p, double* scal, int32_t* cnt,
+                                                  double* hist, int maxiter) {
+    const int64_t c = blockIdx.x, o = c * len;
+    if (cnt[c * 2 + 1]) return;
+    __shared__ double red[64];
+    __shared__ double bc[2];
+    double d1[1] = {0.0};
+    for (int64_t i = threadIdx.x; i < len; i += blockDim.x) d1[0] += p[o + i] * Ap[o + i];
+    block_sum<1>(d1, red);
+    if (threadIdx.x == 0) bc[0] = scal[c * 4 + 0] / d1[0];                   // alpha = gamma / p.Ap
+    __syncthreads();
+    const double alpha = bc[0];
+    double d[2] = {0.0, 0.0};
+    for (int64_t i = threadIdx.x; i < len; i += blockDim.x) {
+        x[o + i] = x[o + i] + alpha * p[o + i];
+        const double ri = r[o + i] - alpha * Ap[o + i];
+        r[o + i] = ri;
+        const double zi = inv_diag ? ri * inv_diag[o + i] : ri;
+        d[0] += ri * zi;
+        d[1] += ri * ri;
+    }
+    block_sum<2>(d, red);
+    if (threadIdx.x == 0) {
+        const double gamma = scal[c * 4 + 0];
+        bc[1] = d[0] / gamma;                                                 // beta
+        scal[c * 4 + 0] = d[0];
+        scal[c * 4 + 1] = d[1];
+        const int k = cnt[c * 2 + 0] + 1;
+        if (k < maxiter) hist[c * (int64_t)maxiter + k] = sqrt(d[1]);
+        cnt[c * 2 + 0] = k;
+        const double rs = inv_diag ? d[1] : d[0];
+        if (!(rs > scal[c * 4 + 3] && k < maxiter)) cnt[c * 2 + 1] = 1;
+    }
+    __syncthreads();
+    const double beta = bc[1];
+    for (int64_t i = threadIdx.x; i < len; i += blockDim.x) {
+        const double zi = inv_diag ? r[o + i] * inv_diag[o + i] : r[o + i];
+        p[o + i] = zi + beta * p[o + i];
+    }
+}
+
 static inline int reduce_grid(int64_t n, int block) {
     int g = grid_for(n, block);
     const int cap = sm_count() * 4;
@@ -333,6 +413,27 @@ int feb200_cg_stage(feb200_stream s, const feb200_cg_state* st, int32_t stage, d
     rc = cg_stage(as_stream(s), st, stage, tol, atol);
     if (rc) return rc;
     FEB_CHECK_LAUNCH("cg_stage");
+    return FEB200_OK;
+}
+
+int feb200_bcg_init(feb200_stream s, int64_t n_copies, int64_t len, const double* b, const double* Ax0, const double* inv_diag,
+                    double* r, double* p, double* scal, int32_t* cnt, double* hist, double tol, double atol,
+                    int32_t maxiter) {
+    FEB_REQUIRE(b && Ax0 && r && p && scal && cnt && hist && n_copies >= 0 && len >= 0 && maxiter >= 0, FEB200_ERR_INVALID,
+                "bcg_init: bad arguments");
+    if (n_copies == 0) return FEB200_OK;
+    k_bcg_init<<<(unsigned int)n_copies, 256, 0, as_stream(s)>>>(len, b, Ax0, inv_diag, r, p, scal, cnt, hist, tol, atol, maxiter);
+    FEB_CHECK_LAUNCH("bcg_init");
+    return FEB200_OK;
+}
+
+int feb200_bcg_step(feb200_stream s, int64_t n_copies, int64_t len, const double* Ap, const double* inv_diag, double* x,
+                    double* r, double* p, double* scal, int32_t* cnt, double* hist, int32_t maxiter) {
+    FEB_REQUIRE(Ap && x && r && p && scal && cnt && hist && n_copies >= 0 && len >= 0, FEB200_ERR_INVALID,
+                "bcg_step: bad arguments");
+    if (n_copies == 0) return FEB200_OK;
+    k_bcg_step<<<(unsigned int)n_copies, 256, 0, as_stream(s)>>>(len, Ap, inv_diag, x, r, p, scal, cnt, hist, maxiter);
+    FEB_CHECK_LAUNCH("bcg_step");
     return FEB200_OK;
 }
 

@@ -94,6 +94,8 @@ SIGNATURES = {
     "feb200_cg_init": (c_int32, [_P, POINTER(CGState), _F64, _F64]),
     "feb200_cg_iterate": (c_int32, [_P, POINTER(CGState), _I32]),
     "feb200_cg_stage": (c_int32, [_P, POINTER(CGState), _I32, _F64, _F64]),
+    "feb200_bcg_init": (c_int32, [_P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _F64, _F64, _I32]),
+    "feb200_bcg_step": (c_int32, [_P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _I32]),
     "feb200_axpby": (c_int32, [_P, _I64, _F64, _P, _F64, _P, _P]),
     "feb200_scatter_set": (c_int32, [_P, _I64, _P, _P, _F64, _P, _P]),
 }

@@ -4,9 +4,11 @@ The reference runs `vmap` over thousands of microscale RVE solves that share a m
 material fields and Dirichlet values (/root/reference/tests/test_microscale_bvp.py,
 tests/test_multiscale_prnn.py).  First cut here: the copies are laid side by side as ONE block-diagonal
 problem (vertices and connectivity replicated with an offset, material parameters concatenated along the
-element axis), so the whole batch goes through the same assembly kernels, one CSR and one CG.  The CG stopping
-test is therefore global over the batch (all copies iterate until the batch residual meets the tolerance);
-per-copy iteration counts are future work.
+element axis), so the whole batch goes through the same assembly kernels and one CSR.  The linear solves run as a
+batched CG (csrc/krylov.cu k_bcg_*: one SpMV over all copies + one launch with a CTA per copy per iteration), so every
+copy has its own alpha / beta, stopping test and iteration count, as under the reference's vmap; the Newton loop is
+shared (it runs until every copy meets the nonlinear tolerances; converged copies receive zero updates).
+`solve_bvp_batched.last_iterations` holds the per-copy CG iteration counts of each Newton iteration.
 """
 from __future__ import annotations
 
@@ -47,5 +49,15 @@ def solve_bvp_batched(vertices_vd, element_batches, element_residual_func, diric
                                     constitutive_model=b.constitutive_model,
                                     material_params=mp.reshape((C * mp.shape[1],) + mp.shape[2:])))
     u0 = None if u_0_bg is None else _np(u_0_bg).reshape(-1)
-    u, res, _ = solve_bvp(verts, batches, element_residual_func, u0, bcs_all, vals.reshape(-1), solver_options=solver_options)
+    from . import solver as _solver
+    _solver._BATCH["copies"], _solver._BATCH["iterations"] = C, []
+    try:
+        u, res, _ = solve_bvp(verts, batches, element_residual_func, u0, bcs_all, vals.reshape(-1),
+                              solver_options=solver_options)
+    finally:
+        solve_bvp_batched.last_iterations = [k.cpu().numpy() for k in _solver._BATCH["iterations"]]
+        _solver._BATCH["copies"], _solver._BATCH["iterations"] = None, []
     return u.reshape(C, V * D), res.reshape(C, V * D)
+
+
+solve_bvp_batched.last_iterations = []

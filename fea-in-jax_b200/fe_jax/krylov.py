@@ -62,6 +62,42 @@ def cg_on_pattern(pat: NodePattern, values, b, x0, tol, atol, maxiter, inv_diag=
     return x, k, hist[:maxiter]
 
 
+def cg_on_pattern_batched(pat: NodePattern, values, b, x0, tol, atol, maxiter, n_copies, inv_diag=None,
+                          poll_every=POLL_EVERY):
+    """CG on `n_copies` independent systems laid side by side on one node pattern (block-diagonal matrix; copy c owns the
+    DoFs [c*len, (c+1)*len)): every copy has its own alpha / beta / stopping test / iteration count, as vmap(cg) of the
+    reference (solve_cg.py:20-137).  Per iteration: one SpMV over all copies + one launch with a CTA per copy.
+    Returns (x, iterations (n_copies,) int32 tensor, history (n_copies, maxiter) tensor)."""
+    dev = values.device
+    n = pat.U * pat.V
+    assert n % n_copies == 0, "the copies must have equal size"
+    ln = n // n_copies
+    x = x0.clone() if x0 is not None else torch.zeros(n, dtype=torch.float64, device=dev)
+    r, p, Ap = (torch.empty(n, dtype=torch.float64, device=dev) for _ in range(3))
+    hist = torch.zeros(n_copies * max(maxiter, 1), dtype=torch.float64, device=dev)
+    scal = torch.zeros(n_copies * 4, dtype=torch.float64, device=dev)
+    cnt = torch.zeros(n_copies * 2, dtype=torch.int32, device=dev)
+
+    def spmv(v, out):
+        _lib.call("feb200_spmv", pat.V, pat.U, _lib.ptr(pat.nindptr), _lib.ptr(pat.nindices), _lib.ptr(values),
+                  _lib.ptr(v), _lib.ptr(out), None, None, 0)
+
+    spmv(x, Ap)
+    _lib.call("feb200_bcg_init", n_copies, ln, _lib.ptr(b), _lib.ptr(Ap), _lib.ptr(inv_diag), _lib.ptr(r), _lib.ptr(p),
+              _lib.ptr(scal), _lib.ptr(cnt), _lib.ptr(hist), float(tol), float(atol), int(maxiter))
+    launched = 0
+    done = cnt.view(n_copies, 2)[:, 1]
+    while launched < maxiter:
+        for _ in range(min(poll_every, maxiter - launched)):
+            spmv(p, Ap)
+            _lib.call("feb200_bcg_step", n_copies, ln, _lib.ptr(Ap), _lib.ptr(inv_diag), _lib.ptr(x), _lib.ptr(r),
+                      _lib.ptr(p), _lib.ptr(scal), _lib.ptr(cnt), _lib.ptr(hist), int(maxiter))
+            launched += 1
+        if bool(done.all().item()):               # the only host<->device sync of the loop
+            break
+    return x, cnt.view(n_copies, 2)[:, 0].clone(), hist.view(n_copies, max(maxiter, 1))[:, :maxiter]
+
+
 def _as_operator(A):
     if callable(A) and not isinstance(A, (COO, CSR, torch.Tensor)):
         return A

@@ -16,7 +16,10 @@ from typing import Callable, Optional
 import torch
 
 from . import _lib
-from .krylov import JacobiPreconditioner, cg_on_pattern
+from .krylov import JacobiPreconditioner, cg_on_pattern, cg_on_pattern_batched
+
+# set by batched.solve_bvp_batched: the system is `copies` independent problems side by side; CG then runs per copy
+_BATCH = {"copies": None, "iterations": []}
 from .mesh import as_device
 from .sparse import apply_dirichlet_bcs_lhs
 
@@ -160,8 +163,15 @@ def linear_solve(residual: Residual, jacobian: Optional[Jacobian], jacobian_diag
     b = (-R_0).contiguous()
     maxiter = solver_options.linear_max_iter if solver_options.linear_solve_type == LinearSolverType.CG_JAX_SCIPY_W_INFO \
         else 10 * b.shape[0]
-    delta_x, k, hist = cg_on_pattern(pat, J.data, b, delta_x, solver_options.linear_relative_tol,
-                                     solver_options.linear_absolute_tol, maxiter, inv_diag)
+    if _BATCH["copies"]:
+        delta_x, ks, hist_c = cg_on_pattern_batched(pat, J.data, b, delta_x, solver_options.linear_relative_tol,
+                                                    solver_options.linear_absolute_tol, maxiter, _BATCH["copies"], inv_diag)
+        _BATCH["iterations"].append(ks)
+        k = int(ks.max().item())
+        hist = torch.sqrt((hist_c ** 2).sum(dim=0))          # batch residual norm per iteration (finished copies keep their last value 0)
+    else:
+        delta_x, k, hist = cg_on_pattern(pat, J.data, b, delta_x, solver_options.linear_relative_tol,
+                                         solver_options.linear_absolute_tol, maxiter, inv_diag)
     info = solver_info_0
     if solver_options.linear_solve_type == LinearSolverType.CG_JAX_SCIPY_W_INFO:
         per_nl = solver_info_0.linear_iterations_per_nonlinear_iteration.clone()

@@ -256,6 +256,19 @@ typedef enum { FEB200_CG_INIT_SPMV = 0, FEB200_CG_INIT_VECTORS = 1, FEB200_CG_IN
                FEB200_CG_PAP = 4, FEB200_CG_UPDATE_XR = 5, FEB200_CG_UPDATE_P = 6 } feb200_cg_stage_id;
 int feb200_cg_stage(feb200_stream s, const feb200_cg_state* st, int32_t stage, double tol, double atol);
 
+/* Batched CG for many small systems on one mesh (vmap(cg) of the reference, solve_cg.py:20-137 under
+ * tests/test_microscale_bvp.py): n_copies independent systems laid side by side, copy c owning the DoFs
+ * [c*len, (c+1)*len) of every vector, the block-diagonal matrix applied with feb200_spmv.  Every copy keeps its own
+ * alpha, beta, iteration count and stopping test.  scal: 4 doubles per copy {gamma, r.r, b.b, atol2}; cnt: 2 int32 per
+ * copy {k, done}; hist: maxiter doubles per copy.  bcg_init: r = b - Ax0, z = M r, p = z and the first loop test;
+ * bcg_step: one CG iteration after the caller's  Ap = A p  (alpha, x, r, z, the dot products, beta, p, loop test in one
+ * launch; finished copies are skipped).  inv_diag == NULL: no preconditioner. */
+int feb200_bcg_init(feb200_stream s, int64_t n_copies, int64_t len, const double* b, const double* Ax0, const double* inv_diag,
+                    double* r, double* p, double* scal, int32_t* cnt, double* hist, double tol, double atol,
+                    int32_t maxiter);
+int feb200_bcg_step(feb200_stream s, int64_t n_copies, int64_t len, const double* Ap, const double* inv_diag, double* x,
+                    double* r, double* p, double* scal, int32_t* cnt, double* hist, int32_t maxiter);
+
 /* fused vector helpers used by linear_solve / Newton (sparse_linear_solve.py:287-292, 527; fea.py:1103) */
 int feb200_axpby(feb200_stream s, int64_t n, double a, const double* x, double b, const double* y, double* out);
 int feb200_scatter_set(feb200_stream s, int64_t n_idx, const int64_t* idx, const double* vals, double scale_vals,

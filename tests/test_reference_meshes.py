@@ -123,10 +123,15 @@ def test_batched_rve_solves_match_individual_solves(fj):
     batch = fj.ElementBatch(fe_type=fe, n_dofs_per_basis=2, connectivity_en=cells, constitutive_model=fj.elastic_isotropic,
                             material_params=mp[0])
     opts = fj.SolverOptions(linear_precond_type=fj.PreconditionerType.JACOBI, linear_max_iter=4000)
+    vals[3] *= 1e-3          # copies of different scale: every copy must meet ITS OWN relative tolerance
     u_b, res_b = fj.solve_bvp_batched(pts, [batch], fj.linear_elasticity_residual, bcs, vals, [mp], solver_options=opts)
     assert u_b.shape == (C, pts.size)
-    for c in (0, 5, 11):
+    k_b = fj.solve_bvp_batched.last_iterations[0]          # per-copy CG iterations of the first Newton iteration
+    assert k_b.shape == (C,) and k_b.min() > 0
+    for c in (0, 3, 5, 11):
         one = fj.ElementBatch(fe_type=fe, n_dofs_per_basis=2, connectivity_en=cells, constitutive_model=fj.elastic_isotropic,
                               material_params=mp[c])
         u1, _, _ = fj.solve_bvp(pts, [one], fj.linear_elasticity_residual, None, bcs, vals[c], solver_options=opts)
         assert rel_err(u_b[c], u1.cpu().numpy()) <= 1e-7
+        k1 = int(fj.solve_bvp.last_info.linear_iterations_per_nonlinear_iteration[0])
+        assert abs(int(k_b[c]) - k1) <= 1, (c, int(k_b[c]), k1)     # same iteration as the stand-alone solve (vmap semantics)
