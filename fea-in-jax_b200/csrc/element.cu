@@ -507,6 +507,9 @@ int feb200_element_residual(feb200_stream s, const feb200_batch* bp, const doubl
     else if (b.D == 2 && b.N == 4) rc = launch_residual_ct<4, 2>(st, b, x_vd, u, mask, values, R_e);
     else if (b.D == 3 && b.N == 4) rc = launch_residual_ct<4, 3>(st, b, x_vd, u, mask, values, R_e);
     else if (b.D == 3 && b.N == 8) rc = launch_residual_ct<8, 3>(st, b, x_vd, u, mask, values, R_e);
+    else if (b.D == 2 && b.N == 6) rc = launch_residual_ct<6, 2>(st, b, x_vd, u, mask, values, R_e);      // tri6
+    else if (b.D == 3 && b.N == 10) rc = launch_residual_ct<10, 3>(st, b, x_vd, u, mask, values, R_e);    // tet10
+    else if (b.D == 2 && b.N == 9) rc = launch_residual_ct<9, 2>(st, b, x_vd, u, mask, values, R_e);      // quad9
     else if (b.D == 2) k_residual_rt<2><<<grid_for(b.E, 64), 64, 0, st>>>(b, x_vd, u, mask, values, R_e);
     else k_residual_rt<3><<<grid_for(b.E, 64), 64, 0, st>>>(b, x_vd, u, mask, values, R_e);
     if (rc) return rc;
@@ -528,8 +531,11 @@ int feb200_element_tangent(feb200_stream s, const feb200_batch* bp, const double
     TangentCfg c;
     const bool cm = (b.layout != LAYOUT_EQM);
     constexpr int PASSES_HEX = 2;
+#ifndef FEB_GENERAL_CT_MAX_NU
+#define FEB_GENERAL_CT_MAX_NU 30      /* general (state-dependent) tangent: longer block rows (hex27, quad9 ...) go to the runtime-N kernel; tet10 (30) spills but is 3x faster compiled */
+#endif
 #define FEB_TANGENT_CASE(NN, DD, PP)                                                                               \
-    if (b.N == NN && b.D == DD) {                                                                                  \
+    if (b.N == NN && b.D == DD && (iso || NN * DD <= FEB_GENERAL_CT_MAX_NU)) {                                     \
         if (iso) {                                                                                                 \
             rc = tangent_cfg(b, 2, c, 128, ((NN / PP) * DD * DD) | 1);                                                   \
             if (rc) return rc;                                                                                     \
@@ -544,6 +550,9 @@ int feb200_element_tangent(feb200_stream s, const feb200_batch* bp, const double
     FEB_TANGENT_CASE(3, 2, 1)
     FEB_TANGENT_CASE(4, 2, 1)
     FEB_TANGENT_CASE(4, 3, 1)
+    FEB_TANGENT_CASE(6, 2, 1)      /* tri6 */
+    FEB_TANGENT_CASE(10, 3, 2)     /* tet10 */
+    FEB_TANGENT_CASE(9, 2, 1)      /* quad9 */
     FEB_TANGENT_CASE(8, 3, PASSES_HEX) {
         rc = tangent_cfg(b, D4, c);     // the generic kernel stages the full D^4 tangent
         if (rc) return rc;
