@@ -383,10 +383,12 @@ static int cg_stage(cudaStream_t cs, const feb200_cg_state* st, int stage, doubl
         case FEB200_CG_INIT_FINALIZE:
             k_cg_init_finalize<<<1, 1, 0, cs>>>(st->scalars, st->counters, st->hist, st->maxiter, pre);
             break;
-        case FEB200_CG_SPMV:     // Ap = A p (+ p.Ap when there are no ownership weights)
+        case FEB200_CG_SPMV:     // Ap = A p and scalars[1] = p.(A p) with the LOCAL product.  Element-partitioned: the global
+                                 // p.Ap is the sum over ranks of p_r.(A_r p_r) (A = sum R_r^T A_r R_r), so the caller all-reduces
+                                 // scalars[1] as it is -- no halo-summed product, no ownership weights, no extra pass
             if (st->V > 0)
                 rc = spmv_dispatch(cs, st->V, st->U, st->nindptr, st->nindices, st->values, st->p, st->Ap, nullptr, r,
-                                   st->counters, st->weights ? nullptr : st->scalars);
+                                   st->counters, st->scalars);
             break;
         case FEB200_CG_PAP:      // weighted p.Ap -> scalars[1] (local; caller all-reduces)
             k_dot<<<reduce_grid(n, 256), 256, 0, cs>>>(n, st->p, st->Ap, st->weights, st->scalars + S_PAP, r, st->counters);

@@ -327,10 +327,9 @@ class DistributedProblem:
         it = 0
         while it < maxiter:
             for _ in range(min(poll_every, maxiter - it)):
-                stage(_lib.CG_SPMV)
+                stage(_lib.CG_SPMV)                            # Ap = A_loc p and the local p.(A_loc p)
                 halo_sum(comm, idx, [s["Ap"] for s in sts], U)
-                stage(_lib.CG_PAP)
-                reduce(1, 2)
+                reduce(1, 2)                                   # global p.Ap = sum over ranks of the local ones
                 stage(_lib.CG_UPDATE_XR)
                 reduce(2, 4)
                 stage(_lib.CG_UPDATE_P)

@@ -249,8 +249,9 @@ typedef struct {
 int feb200_cg_init(feb200_stream s, const feb200_cg_state* st, double tol, double atol);
 int feb200_cg_iterate(feb200_stream s, const feb200_cg_state* st, int32_t n_iters);
 /* The same loop cut into stages, so that an element-partitioned multi-GPU driver can put the interface
- * halo-sum (after the SpMV stages) and the scalar all-reduces (after INIT_VECTORS: scalars[2,3,5]; after PAP:
- * scalars[1]; after UPDATE_XR: scalars[2,3]) between them.  With `weights` the dot products count every DoF
+ * halo-sum (after the SpMV stages) and the scalar all-reduces (after INIT_VECTORS: scalars[2,3,5]; after SPMV:
+ * scalars[1] = p.(A_local p), whose sum over the ranks is the global p.Ap; after UPDATE_XR: scalars[2,3]) between them.
+ * PAP (weighted p.Ap from the halo-summed product) gives the same number and is kept for drivers that want it.  With `weights` the dot products count every DoF
  * once (owned DoFs only). */
 typedef enum { FEB200_CG_INIT_SPMV = 0, FEB200_CG_INIT_VECTORS = 1, FEB200_CG_INIT_FINALIZE = 2, FEB200_CG_SPMV = 3,
                FEB200_CG_PAP = 4, FEB200_CG_UPDATE_XR = 5, FEB200_CG_UPDATE_P = 6 } feb200_cg_stage_id;
