@@ -25,5 +25,6 @@ for it in range(3):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); e0.record()
     for _ in range(reps):
-        _assemble_values(fj.linear_elasticity_residual, ebc, maps, u, mask, vals, out=out, eliminate=True)
+        _assemble_values(fj.linear_elasticity_residual, ebc, maps, u, mask, vals, out=out,
+                         eliminate=os.environ.get("PF_ELIMINATE", "1") != "0")
     e1.record(); torch.cuda.synchronize(); print("fused assemble ms", e0.elapsed_time(e1) / reps)
