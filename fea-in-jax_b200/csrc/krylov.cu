@@ -84,6 +84,198 @@ __global__ void __launch_bounds__(256) k_spmv(int64_t V, const int64_t* __restri
     }
 }
 
+// ---- SpMV fed by bulk asynchronous copies (cp.async.bulk + mbarrier, the TMA engine's 1-D path) ---------------------
+// The row panels of consecutive vertices are contiguous in the reference's CSR order, so a warp asks the copy engine for
+// the panels of SPB_CH consecutive vertices at once (one ~8 KB copy into one of SPB_NB shared-memory buffers, completion
+// on an mbarrier), one chunk ahead of the one it multiplies; neighbour ids and x of the next chunks are gathered into
+// registers meanwhile.  The matrix (98 % of the bytes) never goes through L1 / the LSU request path, which is what bounds
+// the plain kernel (ncu: L1 request slots 81 % busy, long-scoreboard stalls).  Same arithmetic per row as k_spmv, so the
+// results are bit-identical (tested).  Default for U = 3 (FEB200_SPMV_BULK=0 selects k_spmv).  At 200^3: 3.40 ms against
+// 3.70 ms for k_spmv on the same box with 2 vertices per copy, 2 buffers per warp and 2 CTAs x 10 warps per SM; a pure read
+// stream of the same bytes takes 2.45 ms on this GPU (profiles/read_bandwidth.py).  Other configurations in DESIGN.md.
+#ifndef FEB_SPMV_NB
+#define FEB_SPMV_NB 2
+#endif
+#ifndef FEB_SPMV_WARPS
+#define FEB_SPMV_WARPS 10
+#endif
+#ifndef FEB_SPMV_CH
+#define FEB_SPMV_CH 2
+#endif
+#ifndef FEB_SPMV_CTAS
+#define FEB_SPMV_CTAS 2
+#endif
+constexpr int SPB_NB = FEB_SPMV_NB;
+constexpr int SPB_WARPS = FEB_SPMV_WARPS;
+constexpr int SPB_CH = FEB_SPMV_CH;
+constexpr int SPB_MAXDEG = 32;
+constexpr int SPB_BUF_BYTES = SPB_CH * 9 * SPB_MAXDEG * 8 + 32;      // aligned window around the panels of CH vertices
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+
+__global__ void __launch_bounds__(SPB_WARPS * 32, FEB_SPMV_CTAS)
+k_spmv3_bulk(int64_t V, const int64_t* __restrict__ nindptr, const int32_t* __restrict__ nindices,
+             const double* __restrict__ values, const double* __restrict__ x, double* __restrict__ y, double* dot_out,
+             ReduceWs ws, const int32_t* counters, double* scalars) {
+    if (counters && counters[C_DONE]) return;
+    extern __shared__ __align__(16) unsigned char spb_smem[];
+    __shared__ __align__(8) uint64_t bars[SPB_WARPS * SPB_NB];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* my = spb_smem + (size_t)warp * SPB_NB * SPB_BUF_BYTES;
+    uint64_t* mybar = bars + warp * SPB_NB;
+    if (lane == 0) {
+#pragma unroll
+        for (int b = 0; b < SPB_NB; ++b) mbar_init(mybar + b, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+    const int64_t n_chunks = (V + SPB_CH - 1) / SPB_CH;
+    const int64_t W = (int64_t)gridDim.x * SPB_WARPS;
+    const int64_t w0 = (int64_t)blockIdx.x * SPB_WARPS + warp;
+    const int64_t n_mine = (w0 < n_chunks) ? (n_chunks - w0 + W - 1) / W : 0;        // chunks w0, w0 + W, ...
+    const int64_t total_nodes = nindptr[V];
+    const unsigned char* vbase = reinterpret_cast<const unsigned char*>(values);
+
+    // CSR offsets of a chunk: lane l <= CH holds nindptr[a0 + l] (clamped at V)
+    auto load_ptr = [&](int64_t k) -> int64_t {
+        if (k >= n_mine) return 0;
+        const int64_t a = (w0 + k * W) * SPB_CH + (lane <= SPB_CH ? lane : SPB_CH);
+        return nindptr[a < V ? a : V];
+    };
+    // copy request for my k-th chunk into buffer k % NB; false when it has to take the plain path
+    auto issue = [&](int64_t k, int64_t pl) -> bool {
+        const int64_t p0 = __shfl_sync(0xffffffffu, pl, 0), p1 = __shfl_sync(0xffffffffu, pl, SPB_CH);
+        int maxdeg = 0;
+#pragma unroll
+        for (int v = 0; v < SPB_CH; ++v) {
+            const int dv = (int)(__shfl_sync(0xffffffffu, pl, v + 1) - __shfl_sync(0xffffffffu, pl, v));
+            maxdeg = dv > maxdeg ? dv : maxdeg;
+        }
+        const int64_t vs = (72 * p0) & ~(int64_t)15, vend = (72 * p1 + 15) & ~(int64_t)15;
+        if (maxdeg > SPB_MAXDEG || vend > 72 * total_nodes || p1 == p0) return false;
+        if (lane == 0) {
+            const int b = (int)(k % SPB_NB);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier reads of this buffer are done
+            mbar_expect_tx(mybar + b, (uint32_t)(vend - vs));
+            bulk_g2s(my + (size_t)b * SPB_BUF_BYTES, vbase + vs, (uint32_t)(vend - vs), mybar + b);
+        }
+        return true;
+    };
+    // neighbour ids (two chunks ahead) and x (one chunk ahead) into registers, lane = neighbour
+    auto load_nb = [&](int64_t k, int64_t pl, int32_t (&nb)[SPB_CH]) {
+#pragma unroll
+        for (int v = 0; v < SPB_CH; ++v) {
+            const int64_t p0 = __shfl_sync(0xffffffffu, pl, v), p1 = __shfl_sync(0xffffffffu, pl, v + 1);
+            nb[v] = (k < n_mine && lane < p1 - p0 && lane < SPB_MAXDEG) ? nindices[p0 + lane] : -1;
+        }
+    };
+    auto load_x = [&](const int32_t (&nb)[SPB_CH], double (&xv)[SPB_CH][3]) {
+#pragma unroll
+        for (int v = 0; v < SPB_CH; ++v) {
+            xv[v][0] = xv[v][1] = xv[v][2] = 0.0;
+            if (nb[v] >= 0) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) xv[v][j] = x[(int64_t)nb[v] * 3 + j];
+            }
+        }
+    };
+
+    double d = 0.0;
+    unsigned int phase = 0;                                                  // bit b: parity of buffer b's next completion
+    // pipeline registers: offsets of chunks k, k+1, k+2; bulk flags of k, k+1; x of k, k+1
+    int64_t pl0 = load_ptr(0), pl1 = load_ptr(1), pl2 = load_ptr(2);
+    bool bulk0 = n_mine > 0 && issue(0, pl0);
+    bool bulk1 = n_mine > 1 && issue(1, pl1);
+    double xc[SPB_CH][3], xn[SPB_CH][3];
+    int32_t nb1[SPB_CH], nb2[SPB_CH];
+    load_nb(0, pl0, nb1);
+    load_x(nb1, xc);
+    load_nb(1, pl1, nb1);
+    for (int64_t k = 0; k < n_mine; ++k) {
+        const int64_t a0 = (w0 + k * W) * SPB_CH;
+        load_x(nb1, xn);                                                     // chunk k + 1: ids arrived an iteration ago
+        load_nb(k + 2, pl2, nb2);                                            // chunk k + 2
+        const int64_t pl3 = load_ptr(k + 3);
+        bool bulk2 = false;
+        if (SPB_NB >= 3) bulk2 = (k + 2 < n_mine) && issue(k + 2, pl2);      // buffer (k+2) % NB was released two iterations ago
+        if (bulk0) {
+            const int b = (int)(k % SPB_NB);
+            while (!mbar_try_wait(mybar + b, (phase >> b) & 1u)) {}
+            phase ^= 1u << b;
+            const int64_t pbase = __shfl_sync(0xffffffffu, pl0, 0);
+            const unsigned char* buf = my + (size_t)b * SPB_BUF_BYTES + ((72 * pbase) & 15);
+#pragma unroll
+            for (int v = 0; v < SPB_CH; ++v) {
+                const int64_t p0 = __shfl_sync(0xffffffffu, pl0, v), p1 = __shfl_sync(0xffffffffu, pl0, v + 1);
+                const int64_t a = a0 + v;
+                if (a >= V) break;
+                const int deg = (int)(p1 - p0);
+                const int row_len = 3 * deg;
+                const double* val = reinterpret_cast<const double*>(buf + 72 * (p0 - pbase));
+                double acc[3] = {0.0, 0.0, 0.0};
+                if (lane < deg) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) acc[i] += val[i * row_len + 3 * lane + j] * xc[v][j];
+                }
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    acc[i] = warp_sum(acc[i]);
+                    if (lane == 0) {
+                        y[a * 3 + i] = acc[i];
+                        d += x[a * 3 + i] * acc[i];
+                    }
+                }
+            }
+        } else {
+            for (int v = 0; v < SPB_CH; ++v)
+                if (a0 + v < V) d += spmv_vertex<3>(a0 + v, lane, nindptr, nindices, values, x, y);
+        }
+        __syncwarp();
+        if (SPB_NB < 3) {                                                    // double buffering: the buffer just read is the one chunk k + 2 uses
+            bulk2 = (k + 2 < n_mine) && issue(k + 2, pl2);
+        }
+        pl0 = pl1; pl1 = pl2; pl2 = pl3;
+        bulk0 = bulk1; bulk1 = bulk2;
+#pragma unroll
+        for (int v = 0; v < SPB_CH; ++v) nb1[v] = nb2[v];
+#pragma unroll
+        for (int v = 0; v < SPB_CH; ++v)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) xc[v][j] = xn[v][j];
+    }
+    if (!dot_out && !scalars) return;
+    __shared__ double red[32];
+    double dd[1] = {lane == 0 ? d : 0.0};
+    block_sum<1>(dd, red);
+    double total[1];
+    if (grid_sum_last_block<1>(dd, ws.part, ws.ticket, total)) {
+        if (dot_out) dot_out[0] = total[0];
+        if (scalars) scalars[S_PAP] = total[0];
+    }
+}
+
 __global__ void k_spmv_csr(int64_t n_rows, const int64_t* __restrict__ indptr, const int64_t* __restrict__ indices,
                            const double* __restrict__ values, const double* __restrict__ x, double* __restrict__ y) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -301,10 +493,28 @@ static void launch_spmv(cudaStream_t st, int64_t V, const int64_t* nindptr, cons
     k_spmv<U><<<(int)g, 256, 0, st>>>(V, nindptr, nindices, values, x, y, dot_out, ws, counters, scalars);
 }
 
+static bool spmv_bulk_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("FEB200_SPMV_BULK");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
+
 static int spmv_dispatch(cudaStream_t st, int64_t V, int U, const int64_t* nindptr, const int32_t* nindices,
                          const double* values, const double* x, double* y, double* dot_out, ReduceWs ws,
                          const int32_t* counters, double* scalars) {
-    if (U == 3) launch_spmv<3>(st, V, nindptr, nindices, values, x, y, dot_out, ws, counters, scalars);
+    if (U == 3 && spmv_bulk_enabled()) {
+        const size_t smem = (size_t)SPB_WARPS * SPB_NB * SPB_BUF_BYTES;
+        FEB_CUDA(cudaFuncSetAttribute(k_spmv3_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int64_t g = ceil_div(ceil_div(V, SPB_CH), SPB_WARPS);
+        int64_t cap = (int64_t)sm_count() * FEB_SPMV_CTAS;
+        if (dot_out || scalars) cap = MAX_PARTIALS < cap ? MAX_PARTIALS : cap;
+        if (g > cap) g = cap;
+        if (g < 1) g = 1;
+        k_spmv3_bulk<<<(int)g, SPB_WARPS * 32, smem, st>>>(V, nindptr, nindices, values, x, y, dot_out, ws, counters, scalars);
+    } else if (U == 3) launch_spmv<3>(st, V, nindptr, nindices, values, x, y, dot_out, ws, counters, scalars);
     else if (U == 2) launch_spmv<2>(st, V, nindptr, nindices, values, x, y, dot_out, ws, counters, scalars);
     else if (U == 1) launch_spmv<1>(st, V, nindptr, nindices, values, x, y, dot_out, ws, counters, scalars);
     else FEB_REQUIRE(false, FEB200_ERR_UNSUPPORTED, "spmv: U=%d not supported", U);

@@ -27,3 +27,11 @@ for it in range(3):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
     print(f"spmv ms {ms:.4f}  {bytes_ / ms / 1e6:.0f} GB/s  checksum {float(y.sum()):.6e}")
+
+if os.environ.get("PF_CHECK") == "1":           # against the generic CSR kernel on the expanded pattern (small n only)
+    row, col, indptr = pat._expand()
+    y2 = torch.empty_like(y)
+    _lib.call("feb200_spmv_csr", F, _lib.ptr(indptr), _lib.ptr(col), _lib.ptr(vals), _lib.ptr(x), _lib.ptr(y2))
+    spmv()
+    torch.cuda.synchronize()
+    print("max rel diff vs generic CSR kernel:", float((y - y2).abs().max() / y2.abs().max()))

@@ -592,3 +592,43 @@ def test_fused_kernels_on_grid_with_missing_elements(fj, keep):
         assert rel_err(v, d_o) <= ASM_RTOL, impl
     assert rel_err(out["mma"], out["two-pass"].cpu().numpy()) <= 1e-13
     assert torch.equal(out["v4"], out["two-pass"])          # same summation order by construction
+
+
+_SPMV_SCRIPT = r"""
+import os, sys
+root = os.environ['FEB_ROOT']
+sys.path[:0] = [root, os.path.join(root, 'fea-in-jax_b200'), os.path.join(root, 'tests')]
+import numpy as np, torch
+import fe_jax as fj
+from fe_jax.assembly import _assemble_values
+from fe_jax.sparse import pattern_matvec
+from helpers import build_pair, material_params
+from oracle import fe_oracle as orc
+n = 9
+Vx, cells = orc.uniform_hex_grid(n, n + 2, n - 3)
+rng = np.random.default_rng(21)
+Vx = Vx + 0.1 / n * rng.uniform(-1, 1, size=Vx.shape)
+cells = cells[rng.uniform(size=cells.shape[0]) < 0.8]
+mp = material_params('elastic_isotropic', 3, (), seed=1)
+ebc, maps, token, prob, _ = build_pair(fj, Vx, [dict(cell='hexahedron', degree=1, qdeg=2, cells=cells, model='elastic_isotropic', mp=mp)])
+u = torch.zeros(Vx.size, dtype=torch.float64, device='cuda')
+vals, pat = _assemble_values(token, ebc, maps, u)
+x = torch.tensor(rng.normal(size=Vx.size), device='cuda')
+np.save(sys.argv[1], pattern_matvec(pat, vals, x).cpu().numpy())
+"""
+
+
+def test_spmv_bulk_copy_kernel_is_bit_identical_to_plain_kernel(fj, tmp_path):
+    """k_spmv3_bulk (row panels through cp.async.bulk + mbarrier, opt-in with FEB200_SPMV_BULK=1) against k_spmv (plain
+    loads): same per-row arithmetic order, so the products must agree bit for bit; each runs in its own process because
+    the switch is read once.  The mesh has missing elements (ragged degrees, vertices without neighbours)."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    for bulk in ("1", "0"):
+        f = str(tmp_path / f"y_{bulk}.npy")
+        env = dict(os.environ, FEB200_SPMV_BULK=bulk, FEB_ROOT=root, FEB200_QUIET="1")
+        subprocess.run([sys.executable, "-c", _SPMV_SCRIPT, f], check=True, env=env, cwd=root, timeout=600)
+        out[bulk] = np.load(f)
+    assert np.isfinite(out["1"]).all() and np.abs(out["1"]).max() > 0
+    assert np.array_equal(out["1"], out["0"])
