@@ -397,18 +397,36 @@ def main():
     copy_stream = torch.cuda.Stream(device=dev)
     r_ready = torch.cuda.Event()
 
+    u_ready, j_ready = torch.cuda.Event(), torch.cuda.Event()
+
     def e2e_step():
-        # host u -> device; residual; its device->host copy runs on a second stream under the Jacobian kernel;
-        # Jacobian (Dirichlet elimination fused); diagonal -> host.  Both copies finish inside the timed region.
-        u.copy_(u_host, non_blocking=True)
-        R, _ = fj.calculate_residual_w_dirichlet(token, ebc, maps, u, values, mask)
-        r_ready.record()
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(r_ready)
+        # Both copies finish inside the timed region.  Linear elasticity: the tangent does not depend on u, so the
+        # Jacobian kernel starts at once and the host -> device copy of u runs under it on the copy stream; the
+        # diagonal's device -> host copy then runs under the residual kernels and only the residual's copy is exposed.
+        # Hyperelastic: u first, residual, its copy under the tangent + assembly kernels, then the diagonal's copy.
+        if not hyper:
+            with torch.cuda.stream(copy_stream):
+                u.copy_(u_host, non_blocking=True)
+                u_ready.record()
+            _assemble_values(token, ebc, maps, u, mask, values, out=J_vals, eliminate=True)
+            d = csr_diagonal(pat, J_vals)
+            j_ready.record()
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(j_ready)
+                diag_host.copy_(d, non_blocking=True)
+            torch.cuda.current_stream().wait_event(u_ready)
+            R, _ = fj.calculate_residual_w_dirichlet(token, ebc, maps, u, values, mask)
             R_host.copy_(R, non_blocking=True)
-        _assemble_values(token, ebc, maps, u, mask, values, out=J_vals, eliminate=True)
-        d = csr_diagonal(pat, J_vals)
-        diag_host.copy_(d, non_blocking=True)
+        else:
+            u.copy_(u_host, non_blocking=True)
+            R, _ = fj.calculate_residual_w_dirichlet(token, ebc, maps, u, values, mask)
+            r_ready.record()
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(r_ready)
+                R_host.copy_(R, non_blocking=True)
+            _assemble_values(token, ebc, maps, u, mask, values, out=J_vals, eliminate=True)
+            d = csr_diagonal(pat, J_vals)
+            diag_host.copy_(d, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         copy_stream.synchronize()
     e2e_ms, _ = timed(e2e_step, max(1, args.steps), 1)
