@@ -132,6 +132,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 
+// Sums over the warp of the six values A[0..2], B[0..2] at once: after the steps with offsets 16, 8 and 4 every group of
+// four lanes keeps one value (slot = lane >> 2: A0 A1 A2 - B0 B1 B2 -), after 2 and 1 each lane of the group holds its total.
+// Every step adds the same pairs as the butterfly of warp_sum, so each total is bit-identical to warp_sum of that value.
+__device__ __forceinline__ double warp_sum_2x3(const double (&A)[3], const double (&B)[3], int lane) {
+    const bool up = (lane & 16) != 0, hi = (lane & 8) != 0, q = (lane & 4) != 0;
+    double k[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double keep = up ? B[i] : A[i], send = up ? A[i] : B[i];
+        k[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    double m0 = hi ? k[2] : k[0], m1 = hi ? 0.0 : k[1];
+    const double t0 = hi ? k[0] : k[2], t1 = hi ? k[1] : 0.0;
+    m0 += __shfl_xor_sync(0xffffffffu, t0, 8);
+    m1 += __shfl_xor_sync(0xffffffffu, t1, 8);
+    double r = (q ? m1 : m0) + __shfl_xor_sync(0xffffffffu, q ? m0 : m1, 4);
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    return r;
+}
+
 __global__ void __launch_bounds__(SPB_WARPS * 32, FEB_SPMV_CTAS)
 k_spmv3_bulk(int64_t V, const int64_t* __restrict__ nindptr, const int32_t* __restrict__ nindices,
              const double* __restrict__ values, const double* __restrict__ x, double* __restrict__ y, double* dot_out,
@@ -189,7 +210,9 @@ k_spmv3_bulk(int64_t V, const int64_t* __restrict__ nindptr, const int32_t* __re
             nb[v] = (k < n_mine && lane < p1 - p0 && lane < SPB_MAXDEG) ? nindices[p0 + lane] : -1;
         }
     };
-    auto load_x = [&](const int32_t (&nb)[SPB_CH], double (&xv)[SPB_CH][3]) {
+    // x of chunk k at the neighbours (lane = neighbour).  Returns the row's own x for the lane that ends up holding that
+    // row's sum after the transposed reduction below: lane 4 s, s = 4 v + i, holds y[3 (a0 + v) + i]
+    auto load_x = [&](int64_t k, const int32_t (&nb)[SPB_CH], double (&xv)[SPB_CH][3]) -> double {
 #pragma unroll
         for (int v = 0; v < SPB_CH; ++v) {
             xv[v][0] = xv[v][1] = xv[v][2] = 0.0;
@@ -198,6 +221,11 @@ k_spmv3_bulk(int64_t V, const int64_t* __restrict__ nindptr, const int32_t* __re
                 for (int j = 0; j < 3; ++j) xv[v][j] = x[(int64_t)nb[v] * 3 + j];
             }
         }
+        double xo = 0.0;
+        const int sl = lane >> 2;
+        const int64_t a = (w0 + k * W) * SPB_CH + (sl >> 2);
+        if (k < n_mine && (lane & 3) == 0 && (sl & 3) < 3 && (sl >> 2) < SPB_CH && a < V) xo = x[a * 3 + (sl & 3)];
+        return xo;
     };
 
     double d = 0.0;
@@ -209,11 +237,11 @@ k_spmv3_bulk(int64_t V, const int64_t* __restrict__ nindptr, const int32_t* __re
     double xc[SPB_CH][3], xn[SPB_CH][3];
     int32_t nb1[SPB_CH], nb2[SPB_CH];
     load_nb(0, pl0, nb1);
-    load_x(nb1, xc);
+    double xoc = load_x(0, nb1, xc);
     load_nb(1, pl1, nb1);
     for (int64_t k = 0; k < n_mine; ++k) {
         const int64_t a0 = (w0 + k * W) * SPB_CH;
-        load_x(nb1, xn);                                                     // chunk k + 1: ids arrived an iteration ago
+        const double xon = load_x(k + 1, nb1, xn);                     // chunk k + 1: ids arrived an iteration ago
         load_nb(k + 2, pl2, nb2);                                            // chunk k + 2
         const int64_t pl3 = load_ptr(k + 3);
         bool bulk2 = false;
@@ -224,27 +252,42 @@ k_spmv3_bulk(int64_t V, const int64_t* __restrict__ nindptr, const int32_t* __re
             phase ^= 1u << b;
             const int64_t pbase = __shfl_sync(0xffffffffu, pl0, 0);
             const unsigned char* buf = my + (size_t)b * SPB_BUF_BYTES + ((72 * pbase) & 15);
+            double acc[SPB_CH][3];
 #pragma unroll
             for (int v = 0; v < SPB_CH; ++v) {
                 const int64_t p0 = __shfl_sync(0xffffffffu, pl0, v), p1 = __shfl_sync(0xffffffffu, pl0, v + 1);
-                const int64_t a = a0 + v;
-                if (a >= V) break;
-                const int deg = (int)(p1 - p0);
+                const int deg = (int)(p1 - p0);                              // 0 beyond the last vertex (offsets are clamped)
                 const int row_len = 3 * deg;
                 const double* val = reinterpret_cast<const double*>(buf + 72 * (p0 - pbase));
-                double acc[3] = {0.0, 0.0, 0.0};
+                acc[v][0] = acc[v][1] = acc[v][2] = 0.0;
                 if (lane < deg) {
 #pragma unroll
                     for (int i = 0; i < 3; ++i)
 #pragma unroll
-                        for (int j = 0; j < 3; ++j) acc[i] += val[i * row_len + 3 * lane + j] * xc[v][j];
+                        for (int j = 0; j < 3; ++j) acc[v][i] += val[i * row_len + 3 * lane + j] * xc[v][j];
                 }
+            }
+            if (SPB_CH == 2) {
+                // the six row sums of the chunk in one transposed reduction (8 shuffles instead of 30; same addition tree
+                // per row as warp_sum, so the rows stay bit-identical to k_spmv): lane 4 s ends up with row s = 4 v + i
+                const double rsum = warp_sum_2x3(acc[0], acc[SPB_CH - 1], lane);
+                const int sl = lane >> 2;
+                if ((lane & 3) == 0 && (sl & 3) < 3 && a0 + (sl >> 2) < V) {
+                    y[(a0 + (sl >> 2)) * 3 + (sl & 3)] = rsum;
+                    d += xoc * rsum;
+                }
+            } else {
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    acc[i] = warp_sum(acc[i]);
-                    if (lane == 0) {
-                        y[a * 3 + i] = acc[i];
-                        d += x[a * 3 + i] * acc[i];
+                for (int v = 0; v < SPB_CH; ++v) {
+                    const int64_t a = a0 + v;
+                    if (a >= V) break;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        acc[v][i] = warp_sum(acc[v][i]);
+                        if (lane == 0) {
+                            y[a * 3 + i] = acc[v][i];
+                            d += x[a * 3 + i] * acc[v][i];
+                        }
                     }
                 }
             }
@@ -264,10 +307,11 @@ k_spmv3_bulk(int64_t V, const int64_t* __restrict__ nindptr, const int32_t* __re
         for (int v = 0; v < SPB_CH; ++v)
 #pragma unroll
             for (int j = 0; j < 3; ++j) xc[v][j] = xn[v][j];
+        xoc = xon;
     }
     if (!dot_out && !scalars) return;
     __shared__ double red[32];
-    double dd[1] = {lane == 0 ? d : 0.0};
+    double dd[1] = {d};                                                      // partial sums sit on the lanes 4 s (and lane 0)
     block_sum<1>(dd, red);
     double total[1];
     if (grid_sum_last_block<1>(dd, ws.part, ws.ticket, total)) {
