@@ -521,25 +521,27 @@ k_fused_hex8_mma(feb200_batch b, feb200_fused_plan plan, MmaSmem L, const double
                     const unsigned int bsel = (src[v] >> (4 * k)) & 0xfu;
                     const int t = (int)(((k < 4 ? tk[v].x : tk[v].y) >> (8 * (k & 3))) & 0xffu);
                     const bool on = (bsel != 0xfu) && (av[v] >= 0);
-                    const double* sp = stage + (size_t)t * MM_IS + bsel * 3;       // absent contributions: predicated-off loads
-#define MM_LD(x) (on ? (x) : 0.0)
+                    // absent contributions: load and addition are both predicated off.  (The select form
+                    // `acc += on ? x : 0.0` compiled to a zero-fill per load plus a copy of the accumulator on the FP64 pipe.)
+                    const double* sp = stage + (size_t)t * MM_IS + bsel * 3;
                     if (UNIFORM) {
 #pragma unroll
                         for (int i = 0; i < 3; ++i)
 #pragma unroll
-                            for (int j = 0; j < 3; ++j) acc[v][i * 3 + j] += MM_LD(sp[i * 24 + j]);
+                            for (int j = 0; j < 3; ++j)
+                                if (on) acc[v][i * 3 + j] += sp[i * 24 + j];
                     } else {
                         const double rho = on ? xs[(itw_s[t] & 0xfffu) * MM_XS + 25] : 0.0;
 #pragma unroll
                         for (int i = 0; i < 3; ++i)
 #pragma unroll
-                            for (int j = 0; j < 3; ++j) {
-                                const double val = MM_LD(sp[i * 24 + j]);
-                                acc[v][i * 3 + j] += val;
-                                accl[UNIFORM ? 0 : v][i * 3 + j] += rho * val;
-                            }
+                            for (int j = 0; j < 3; ++j)
+                                if (on) {
+                                    const double val = sp[i * 24 + j];
+                                    acc[v][i * 3 + j] += val;
+                                    accl[UNIFORM ? 0 : v][i * 3 + j] += rho * val;
+                                }
                     }
-#undef MM_LD
                 }
             }
 #pragma unroll
