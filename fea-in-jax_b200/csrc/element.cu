@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(BLOCK, FEB_RES_MINBLOCKS) k_residual_ct(feb200
     for (int64_t e0 = (int64_t)blockIdx.x * BLOCK; e0 < b.E; e0 += (int64_t)gridDim.x * BLOCK) {
         const int64_t e = e0 + threadIdx.x;
         if (e < b.E) {
-            double x[NU], ue[NU], R[NU], g[NU];
+            double x[NU], ue[NU], R[NU];
 #pragma unroll
             for (int n = 0; n < N; ++n) {
                 const int64_t v = b.conn[e * N + n];
@@ -59,29 +59,56 @@ __global__ void __launch_bounds__(BLOCK, FEB_RES_MINBLOCKS) k_residual_ct(feb200
                 for (int i = 0; i < NU; ++i) ue[i] += x[i];
             int qs;
             const double* mp = mp_of(b, e, qs);
+            // Per point, in reference coordinates: the physical gradients g[n][d] = sum_p Ji[d][p] dphi[n][p] are never
+            // formed (24 fewer live doubles for hex8).  H[i][d] = sum_n u[n][i] g[n][d] = sum_p Hr[i][p] Ji[d][p] with
+            // Hr = sum_n u[n] (x) dphi[n];  R[n][d] += w sum_i g[n][i] S[i][d] = sum_p dphi[n][p] T[p][d] with
+            // T = w Ji^T S.  Same quantities as linear_elasticity.py:145-206 / hyperelasticity.py:93-139.
             for (int q = 0; q < b.Q; ++q) {
-                const double dt = shape_gradients<N, D>(x, s_dphi + q * NU, g);
-                double H[D][D], S[D][D];
+                const volatile double* dq = s_dphi + q * NU;            // in program order: hoisting all 2 NU loads spills
+                double J[D][D], Ji[D][D], Hr[D][D], H[D][D], S[D][D], T[D][D];
+#pragma unroll
+                for (int p = 0; p < D; ++p)
+#pragma unroll
+                    for (int d = 0; d < D; ++d) { J[p][d] = 0.0; Hr[p][d] = 0.0; }
+#pragma unroll
+                for (int n = 0; n < N; ++n)
+#pragma unroll
+                    for (int p = 0; p < D; ++p) {
+                        const double dp = dq[n * D + p];
+#pragma unroll
+                        for (int d = 0; d < D; ++d) {
+                            J[p][d] += x[n * D + d] * dp;
+                            Hr[d][p] += ue[n * D + d] * dp;
+                        }
+                    }
+                const double dt = inverse(J, Ji);                           // Ji[d][p] = d xi_p / d x_d
 #pragma unroll
                 for (int i = 0; i < D; ++i)
-#pragma unroll
-                    for (int d = 0; d < D; ++d) H[i][d] = 0.0;
-#pragma unroll
-                for (int n = 0; n < N; ++n)
-#pragma unroll
-                    for (int i = 0; i < D; ++i)
-#pragma unroll
-                        for (int d = 0; d < D; ++d) H[i][d] += g[n * D + d] * ue[n * D + i];
-                point_stress<D, double>(b.material, mp + (int64_t)q * qs, H, S);
-                const double w = dt * s_W[q];
-#pragma unroll
-                for (int n = 0; n < N; ++n)
 #pragma unroll
                     for (int d = 0; d < D; ++d) {
                         double sacc = 0.0;
 #pragma unroll
-                        for (int i = 0; i < D; ++i) sacc += g[n * D + i] * S[i][d];
-                        R[n * D + d] += w * sacc;
+                        for (int p = 0; p < D; ++p) sacc += Hr[i][p] * Ji[d][p];
+                        H[i][d] = sacc;
+                    }
+                point_stress<D, double>(b.material, mp + (int64_t)q * qs, H, S);
+                const double w = dt * s_W[q];
+#pragma unroll
+                for (int p = 0; p < D; ++p)
+#pragma unroll
+                    for (int d = 0; d < D; ++d) {
+                        double sacc = 0.0;
+#pragma unroll
+                        for (int i = 0; i < D; ++i) sacc += Ji[i][p] * S[i][d];
+                        T[p][d] = w * sacc;
+                    }
+#pragma unroll
+                for (int n = 0; n < N; ++n)
+#pragma unroll
+                    for (int p = 0; p < D; ++p) {
+                        const double dp = dq[n * D + p];
+#pragma unroll
+                        for (int d = 0; d < D; ++d) R[n * D + d] += dp * T[p][d];
                     }
             }
 #pragma unroll

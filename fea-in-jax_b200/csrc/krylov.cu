@@ -392,18 +392,46 @@ __global__ void k_cg_init_finalize(double* scalars, int32_t* counters, double* h
 __global__ void __launch_bounds__(256) k_cg_update_xr(int64_t n, const double* __restrict__ p, const double* __restrict__ Ap,
                                                       const double* __restrict__ inv_diag, const double* __restrict__ w,
                                                       double* __restrict__ x, double* __restrict__ r, double* scalars,
-                                                      const int32_t* counters, ReduceWs ws) {
+                                                      const int32_t* counters, ReduceWs ws, int vec2) {
     if (counters[C_DONE]) return;
     const double alpha = scalars[S_GAMMA] / scalars[S_PAP];
     double d[2] = {0.0, 0.0};
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        x[i] = x[i] + alpha * p[i];
-        const double ri = r[i] - alpha * Ap[i];
-        r[i] = ri;
-        const double zi = inv_diag ? ri * inv_diag[i] : ri;
+    auto one = [&](int64_t i) {
+        x[i] = __fma_rn(alpha, p[i], x[i]);            // explicit roundings: a DoF must get the same bits whether it
+        const double ri = __fma_rn(-alpha, Ap[i], r[i]);  // sits in the .x / .y half of a pair or in the scalar tail (the
+        r[i] = ri;                                       // copies of an interface DoF on two ranks do)
+        const double zi = inv_diag ? __dmul_rn(ri, inv_diag[i]) : ri;
         const double wi = w ? w[i] : 1.0;
         d[0] += wi * (ri * zi);
         d[1] += wi * (ri * ri);
+    };
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    if (vec2) {                                    // 16-byte accesses (all vectors 16-byte aligned, checked by the host side)
+        const double2* p2 = reinterpret_cast<const double2*>(p);
+        const double2* A2 = reinterpret_cast<const double2*>(Ap);
+        const double2* i2 = reinterpret_cast<const double2*>(inv_diag);
+        const double2* w2 = reinterpret_cast<const double2*>(w);
+        double2* x2 = reinterpret_cast<double2*>(x);
+        double2* r2 = reinterpret_cast<double2*>(r);
+        const int64_t n2 = n >> 1;
+        for (int64_t i = tid; i < n2; i += stride) {
+            const double2 pv = p2[i], av = A2[i];
+            double2 xv = x2[i], rv = r2[i];
+            xv.x = __fma_rn(alpha, pv.x, xv.x); xv.y = __fma_rn(alpha, pv.y, xv.y);
+            rv.x = __fma_rn(-alpha, av.x, rv.x); rv.y = __fma_rn(-alpha, av.y, rv.y);
+            x2[i] = xv;
+            r2[i] = rv;
+            double2 zv = rv, wv = make_double2(1.0, 1.0);
+            if (inv_diag) { const double2 iv = i2[i]; zv.x = __dmul_rn(zv.x, iv.x); zv.y = __dmul_rn(zv.y, iv.y); }
+            if (w) wv = w2[i];
+            d[0] += wv.x * (rv.x * zv.x);
+            d[1] += wv.x * (rv.x * rv.x);
+            d[0] += wv.y * (rv.y * zv.y);
+            d[1] += wv.y * (rv.y * rv.y);
+        }
+        if ((n & 1) && tid == 0) one(n - 1);
+    } else {
+        for (int64_t i = tid; i < n; i += stride) one(i);
     }
     __shared__ double red[64];
     block_sum<2>(d, red);
@@ -417,12 +445,33 @@ __global__ void __launch_bounds__(256) k_cg_update_xr(int64_t n, const double* _
 // p = z + beta p
 __global__ void __launch_bounds__(256) k_cg_update_p(int64_t n, const double* __restrict__ r,
                                                      const double* __restrict__ inv_diag, double* __restrict__ p,
-                                                     const double* scalars, const int32_t* counters) {
+                                                     const double* scalars, const int32_t* counters, int vec2) {
     if (counters[C_DONE]) return;
     const double beta = scalars[S_GAMMA_NEW] / scalars[S_GAMMA];
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const double zi = inv_diag ? r[i] * inv_diag[i] : r[i];
-        p[i] = zi + beta * p[i];
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    if (vec2) {
+        const double2* r2 = reinterpret_cast<const double2*>(r);
+        const double2* i2 = reinterpret_cast<const double2*>(inv_diag);
+        double2* p2 = reinterpret_cast<double2*>(p);
+        const int64_t n2 = n >> 1;
+        for (int64_t i = tid; i < n2; i += stride) {
+            double2 zv = r2[i];
+            if (inv_diag) { const double2 iv = i2[i]; zv.x = __dmul_rn(zv.x, iv.x); zv.y = __dmul_rn(zv.y, iv.y); }
+            double2 pv = p2[i];
+            pv.x = __fma_rn(beta, pv.x, zv.x);         // z rounded first, then one fused step: the same in every path
+            pv.y = __fma_rn(beta, pv.y, zv.y);
+            p2[i] = pv;
+        }
+        if ((n & 1) && tid == 0) {
+            const int64_t i = n - 1;
+            const double zi = inv_diag ? __dmul_rn(r[i], inv_diag[i]) : r[i];
+            p[i] = __fma_rn(beta, p[i], zi);
+        }
+        return;
+    }
+    for (int64_t i = tid; i < n; i += stride) {
+        const double zi = inv_diag ? __dmul_rn(r[i], inv_diag[i]) : r[i];
+        p[i] = __fma_rn(beta, p[i], zi);
     }
 }
 // loop state update (separate tiny kernel: every block of update_p has read gamma before it changes):
@@ -621,6 +670,9 @@ static int cg_stage(cudaStream_t cs, const feb200_cg_state* st, int stage, doubl
     const int64_t n = st->V * st->U;
     ReduceWs r = reduce_ws(st->ws);
     const int pre = st->inv_diag ? 1 : 0;
+    // 16-byte accesses in the vector kernels when every vector they touch is 16-byte aligned
+    const int vec2 = (((uintptr_t)st->x | (uintptr_t)st->r | (uintptr_t)st->p | (uintptr_t)st->Ap | (uintptr_t)st->inv_diag |
+                       (uintptr_t)st->weights) & 15u) == 0;
     int rc = FEB200_OK;
     switch (stage) {
         case FEB200_CG_INIT_SPMV:
@@ -649,10 +701,10 @@ static int cg_stage(cudaStream_t cs, const feb200_cg_state* st, int stage, doubl
             break;
         case FEB200_CG_UPDATE_XR:
             k_cg_update_xr<<<reduce_grid(n, 256), 256, 0, cs>>>(n, st->p, st->Ap, st->inv_diag, st->weights, st->x, st->r,
-                                                              st->scalars, st->counters, r);
+                                                              st->scalars, st->counters, r, vec2);
             break;
         case FEB200_CG_UPDATE_P:
-            k_cg_update_p<<<grid_for(n, 256), 256, 0, cs>>>(n, st->r, st->inv_diag, st->p, st->scalars, st->counters);
+            k_cg_update_p<<<reduce_grid(n, 256), 256, 0, cs>>>(n, st->r, st->inv_diag, st->p, st->scalars, st->counters, vec2);
             k_cg_advance<<<1, 1, 0, cs>>>(st->scalars, st->counters, st->hist, pre);
             break;
         default:
