@@ -96,6 +96,13 @@ __global__ void __launch_bounds__(256) k_spmv(int64_t V, const int64_t* __restri
 #ifndef FEB_SPMV_NB
 #define FEB_SPMV_NB 2
 #endif
+// The copy into a buffer is issued after every lane has consumed its values of that buffer (the row sums went through the
+// warp reduction and a __syncwarp since), so the shared-memory reads are complete and the asynchronous write cannot race
+// them; a proxy fence before the copy is not needed for this read-then-overwrite order, and it costs a MEMBAR.ALL.CTA that
+// waits for the warp's outstanding global prefetch loads.  FEB_SPMV_WAR_FENCE=1 puts it back.
+#ifndef FEB_SPMV_WAR_FENCE
+#define FEB_SPMV_WAR_FENCE 0
+#endif
 #ifndef FEB_SPMV_WARPS
 #define FEB_SPMV_WARPS 10
 #endif
@@ -196,7 +203,9 @@ k_spmv3_bulk(int64_t V, const int64_t* __restrict__ nindptr, const int32_t* __re
         if (maxdeg > SPB_MAXDEG || vend > 72 * total_nodes || p1 == p0) return false;
         if (lane == 0) {
             const int b = (int)(k % SPB_NB);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier reads of this buffer are done
+#if FEB_SPMV_WAR_FENCE
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // (compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC)
+#endif
             mbar_expect_tx(mybar + b, (uint32_t)(vend - vs));
             bulk_g2s(my + (size_t)b * SPB_BUF_BYTES, vbase + vs, (uint32_t)(vend - vs), mybar + b);
         }
