@@ -490,6 +490,7 @@ k_fused_hex8_mma(feb200_batch b, feb200_fused_plan plan, MmaSmem L, const double
         //         the phase is bound by dependent-issue latency, not by any pipe)
         bool fetched_c = false;
         int n_done = 0;
+        if (FEB_MM_LEVELC_AFTER == 0 && has_next) { level_c(); fetched_c = true; }   // before the first vertex group
         for (int a0 = warp; a0 < TN; a0 += MM_BV * MM_WARPS) {
             const int r = lane;
             int av[MM_BV], meta[MM_BV];

@@ -117,3 +117,42 @@ def test_product_does_not_import_oracle():
         if f.endswith(".py"):
             src = open(os.path.join(pkg, f)).read()
             assert "oracle" not in src.replace("# oracle", ""), f"{f} mentions the oracle"
+
+
+def test_transposed_warp_reduction_adds_the_same_pairs_as_the_butterfly():
+    """csrc/krylov.cu warp_sum_2x3: the six row sums of a 2-vertex chunk go through one transposed reduction (8 shuffles).
+    Emulated lane by lane here: every total must be bit-identical to the xor-butterfly warp_sum of the same value, which
+    is what keeps k_spmv3_bulk bit-identical to k_spmv (GPU test test_spmv_bulk_copy_kernel_is_bit_identical...)."""
+    import numpy as np
+    rng = np.random.default_rng(5)
+    lanes = np.arange(32)
+
+    def shfl_xor(v, o):
+        return v[lanes ^ o]
+
+    def butterfly(v):
+        v = v.copy()
+        for o in (16, 8, 4, 2, 1):
+            v = v + shfl_xor(v, o)
+        return v
+
+    for trial in range(20):
+        A = rng.normal(size=(3, 32)) * 10.0 ** rng.integers(-8, 8, size=(3, 32))
+        B = rng.normal(size=(3, 32)) * 10.0 ** rng.integers(-8, 8, size=(3, 32))
+        if trial % 3 == 0:                       # lanes beyond the degree hold zeros
+            A[:, 27:] = 0.0
+            B[:, 18:] = 0.0
+        up, hi, q = (lanes & 16) != 0, (lanes & 8) != 0, (lanes & 4) != 0
+        k = [np.where(up, B[i], A[i]) + shfl_xor(np.where(up, A[i], B[i]), 16) for i in range(3)]
+        m0 = np.where(hi, k[2], k[0]) + shfl_xor(np.where(hi, k[0], k[2]), 8)
+        m1 = np.where(hi, 0.0, k[1]) + shfl_xor(np.where(hi, k[1], 0.0), 8)
+        r = np.where(q, m1, m0) + shfl_xor(np.where(q, m0, m1), 4)
+        r = r + shfl_xor(r, 2)
+        r = r + shfl_xor(r, 1)
+        want = [butterfly(A[0]), butterfly(A[1]), butterfly(A[2]), None, butterfly(B[0]), butterfly(B[1]), butterfly(B[2]), None]
+        for s, w in enumerate(want):
+            if w is None:
+                continue
+            got = r[4 * s:4 * s + 4]
+            assert np.array_equal(got, np.full(4, w[0])), (trial, s)
+            assert np.array_equal(w, np.full(32, w[0]))          # the butterfly leaves the same total on every lane
