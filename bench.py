@@ -4,12 +4,14 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--grid 200] [--impl feb200|reference]
 
 N=1 workload (BASELINE.json configs[1]): 3-D hex8 linear elasticity on a uniform n^3 grid (n=200: 8 M
-elements, 24.4 M DoFs, 1.95e9 non-zeros), interior nodes jittered, batch-constant isotropic material.
+elements, 24.4 M DoFs, 1.95e9 non-zeros), interior nodes jittered, isotropic material with a Young's modulus per
+quadrature point (--layout EQM, the default; M / EM = one material for the batch / per element).
 One "step" = one assembly pass of the whole mesh through the fe_jax call surface:
 calculate_residual_w_dirichlet + Jacobian CSR values at u_w + Dirichlet elimination of the matrix.
 `value` = elements / s with all inputs resident in HBM (CUDA events around the timed region);
 `e2e` = the same pass with the solution vector coming from pinned host memory and the residual + Jacobian
-diagonal read back to the host inside the timed region.  The Newton-CG step (assembly + 100 CG iterations
+diagonal read back to the host inside the timed region (copies on a second stream: u's under the Jacobian kernel,
+which does not read u for linear elasticity, the diagonal's under the residual kernels).  The Newton-CG step (assembly + 100 CG iterations
 + update + residual) is reported in `newton_cg`.  N>1 (torchrun): every rank assembles its own x-slab
 of an (N*n) x n x n grid (weak scaling, no data-path collective in assembly); `newton_cg` then uses the
 NCCL halo-sum + all-reduce path.
