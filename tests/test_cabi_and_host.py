@@ -156,3 +156,19 @@ def test_transposed_warp_reduction_adds_the_same_pairs_as_the_butterfly():
             got = r[4 * s:4 * s + 4]
             assert np.array_equal(got, np.full(4, w[0])), (trial, s)
             assert np.array_equal(w, np.full(32, w[0]))          # the butterfly leaves the same total on every lane
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): one JSON line with the metric, unit,
+    config and the cpu_baseline / e2e objects of the task contract, on a small bounded sample."""
+    import json, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-n", "6"], check=True, capture_output=True, text=True, timeout=600, cwd=root).stdout
+    line = json.loads(out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "elements/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["n_gpus"] == 1 and line["dtype"] == "f64"
+    assert "workload" in line["config"]
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
