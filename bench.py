@@ -319,9 +319,14 @@ def main():
         "scatter_sum": lambda: _lib.call("feb200_scatter_sum", _lib.ptr(row), _lib.ptr(col), V, 3, _lib.ptr(R_e),
                                          _lib.ptr(Rtmp), 0, _lib.ptr(mask), _lib.ptr(values), _lib.ptr(u)),
     }
-    from fe_jax.assembly import _use_tensor_core_kernel, _material_hints
-    use_mma = fused is not None and _use_tensor_core_kernel(ebc, 0, bstruct, fused)
-    if use_mma:
+    from fe_jax.assembly import _use_tensor_core_kernel, _use_sweep_kernel, _material_hints
+    sweep = plan.sweep_plan(ebc, 0) if (not hyper and _use_sweep_kernel(ebc, 0, bstruct)) else None
+    use_mma = sweep is None and fused is not None and _use_tensor_core_kernel(ebc, 0, bstruct, fused)
+    if sweep is not None:
+        kernels["assemble_fused_hex8"] = lambda: _lib.call(
+            "feb200_assemble_fused_hex8_sweep", bstruct, sweep.struct, _lib.ptr(ebc._vertices), _lib.ptr(plan.slot_rank[0]),
+            _lib.ptr(pat.nindices), _lib.ptr(vflags), _material_hints(ebc, 0, bstruct), _lib.ptr(J_vals))
+    elif use_mma:
         kernels["assemble_fused_hex8"] = lambda: _lib.call(
             "feb200_assemble_fused_hex8_mma", bstruct, fused.struct, _lib.ptr(ebc._vertices), _lib.ptr(plan.slot_rank[0]),
             _lib.ptr(pat.nindices), _lib.ptr(vflags), _material_hints(ebc, 0, bstruct), _lib.ptr(J_vals))
@@ -445,7 +450,8 @@ def main():
         bytes_J = 8 * nnz + 2 * 64 * E + 4 * 8 * E + 8 * 3 * V + 8 * n_mp
         alg_bytes = bytes_J + 8 * F + 8 * F + 16 * F + 8 * n_mp
         if "assemble_fused_hex8" in kernel_ms:
-            dom = ("feb200_assemble_fused_hex8_mma (k_fused_hex8_mma)" if use_mma
+            dom = ("feb200_assemble_fused_hex8_sweep (k_fused_hex8_sweep)" if sweep is not None
+                   else "feb200_assemble_fused_hex8_mma (k_fused_hex8_mma)" if use_mma
                    else "feb200_assemble_fused_hex8 (k_fused_hex8_iso)")
             dom_ms = kernel_ms["assemble_fused_hex8"]
         else:

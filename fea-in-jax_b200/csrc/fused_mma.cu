@@ -25,6 +25,7 @@
 // or slot-pairing B phases -- all slower than this configuration.
 #include "common.cuh"
 #include "element_math.cuh"
+#include "hex8_mma.cuh"
 
 #ifndef FEB_MM_LEVELC_AFTER
 #define FEB_MM_LEVELC_AFTER 1        /* B phase: issue the coordinate prefetch after this many vertices of the warp */
@@ -119,45 +120,6 @@ struct MmaPrefetch {
     uint32_t flgb[MM_PN];    // C
     uint4 rk8;               // C
 };
-
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double bb) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(bb));
-}
-
-// Gradients of the 8 shape functions at one quadrature point (same arithmetic as shape_gradients<8,3>, 16-byte loads).
-__device__ __forceinline__ double hex8_gradients(const double* __restrict__ xe, const double* __restrict__ dq, double (&g)[24]) {
-    const double2* x2 = reinterpret_cast<const double2*>(xe);
-    const double2* d2 = reinterpret_cast<const double2*>(dq);
-    double d[24];
-    double J[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
-#pragma unroll
-    for (int h = 0; h < 4; ++h) {                            // two nodes = three double2 per step
-        const double2 xa = x2[3 * h], xb = x2[3 * h + 1], xc = x2[3 * h + 2];
-        const double2 da = d2[3 * h], db = d2[3 * h + 1], dc = d2[3 * h + 2];
-        const double x[6] = {xa.x, xa.y, xb.x, xb.y, xc.x, xc.y};
-        d[6 * h] = da.x; d[6 * h + 1] = da.y; d[6 * h + 2] = db.x; d[6 * h + 3] = db.y; d[6 * h + 4] = dc.x; d[6 * h + 5] = dc.y;
-#pragma unroll
-        for (int m = 0; m < 2; ++m)
-#pragma unroll
-            for (int pp = 0; pp < 3; ++pp)
-#pragma unroll
-                for (int dd = 0; dd < 3; ++dd) J[pp][dd] += x[3 * m + dd] * d[6 * h + 3 * m + pp];
-    }
-    double Ji[3][3];
-    const double dt = inverse(J, Ji);
-#pragma unroll
-    for (int n = 0; n < 8; ++n)
-#pragma unroll
-        for (int dd = 0; dd < 3; ++dd) {
-            double sacc = 0.0;
-#pragma unroll
-            for (int pp = 0; pp < 3; ++pp) sacc += Ji[dd][pp] * d[n * 3 + pp];
-            g[n * 3 + dd] = sacc;
-        }
-    return dt;
-}
 
 // The same for the four nodes 4h .. 4h+3 only (lane = (element, point, node half) when a warp step covers two elements).
 __device__ __forceinline__ double hex8_gradients_half(const double* __restrict__ xe, const double* __restrict__ dq, int h,

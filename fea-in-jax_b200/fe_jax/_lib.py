@@ -44,6 +44,12 @@ class FusedPlan(Structure):
                 ("tile_node_p0", c_void_p), ("tile_node_meta", c_void_p)]
 
 
+class SweepPlan(Structure):
+    _fields_ = [("n_segments", c_int32), ("max_deg", c_int32), ("reserved0", c_int32), ("reserved1", c_int32),
+                ("seg_visit_ptr", c_void_p), ("seg_chunk_ptr", c_void_p), ("visits", c_void_p),
+                ("chunk_v", c_void_p), ("chunk_p0", c_void_p), ("chunk_deg", c_void_p)]
+
+
 class CGState(Structure):
     _fields_ = [("V", c_int64), ("U", c_int32), ("maxiter", c_int32),
                 ("nindptr", c_void_p), ("nindices", c_void_p), ("values", c_void_p), ("inv_diag", c_void_p),
@@ -80,6 +86,8 @@ SIGNATURES = {
     "feb200_assemble_fused_hex8": (c_int32, [_P, POINTER(Batch), POINTER(FusedPlan), _P, _P, _P, _P, _P, _P, _P]),
     "feb200_fused_mma_smem_bytes": (_SZ, [_I32, _I32, _I32]),
     "feb200_assemble_fused_hex8_mma": (c_int32, [_P, POINTER(Batch), POINTER(FusedPlan), _P, _P, _P, _P, _I32, _P]),
+    "feb200_fused_sweep_warps": (c_int32, [_I32]),
+    "feb200_assemble_fused_hex8_sweep": (c_int32, [_P, POINTER(Batch), POINTER(SweepPlan), _P, _P, _P, _P, _I32, _P]),
     "feb200_dirichlet_lhs": (c_int32, [_P, _I64, _I32, _P, _P, _P, _P]),
     "feb200_dirichlet_lhs_coo": (c_int32, [_P, _I64, _P, _P, _P, _P, _P]),
     "feb200_csr_diagonal": (c_int32, [_P, _I64, _I32, _P, _P, _P, _P]),

@@ -283,6 +283,19 @@ class _Plan:
                       _lib.ptr(nindices), _lib.ptr(sr))
             self.slot_rank.append(sr)
         self._fused = {}
+        self._sweep = {}
+
+    def sweep_plan(self, ebc, i):
+        """Streaming plan of feb200_assemble_fused_hex8_sweep for batch i (None when the mesh is not eligible)."""
+        if i not in self._sweep:
+            plan = None
+            if (os.environ.get("FEB200_FUSED", "1") != "0" and ebc.B == 1 and ebc.N[i] == 8 and ebc.Q[i] == 8
+                    and ebc.D == 3 and self.pattern.max_deg <= 32):
+                from .sweep_plan import build_sweep_plan
+                row, col = self._keep[i]
+                plan = build_sweep_plan(ebc._vertices, ebc._conn32[i], row, col, self.pattern.nindptr)
+            self._sweep[i] = plan
+        return self._sweep[i]
 
     def fused_plan(self, ebc, i):
         """Tile plan of the fused hex8 kernel for batch i (None when the batch / mesh is not eligible)."""
@@ -378,7 +391,15 @@ def _assemble_values(element_residual_func, ebc, assembly_map_b, u, mask=None, v
     vals = out if out is not None else torch.empty(pat.nnz, dtype=torch.float64, device=u.device)
     for i in range(ebc.B):
         b = ebc._batch_struct(i, res.kind)
-        # fused path: linear isotropic hex8 (any material layout), single batch (tangent independent of u)
+        # fused paths: linear isotropic hex8 (any material layout), single batch (tangent independent of u).
+        # Streaming kernel when the batch has one Poisson ratio, else the tile kernels.
+        if (b.kind == _lib.KIND_LINEAR and b.material == _lib.MAT_ISOTROPIC and _use_sweep_kernel(ebc, i, b)
+                and plan.sweep_plan(ebc, i) is not None):
+            flags = _vertex_flags(ebc, mask) if (eliminate and mask is not None) else None
+            _lib.call("feb200_assemble_fused_hex8_sweep", b, plan.sweep_plan(ebc, i).struct, _lib.ptr(ebc._vertices),
+                      _lib.ptr(plan.slot_rank[i]), _lib.ptr(pat.nindices), _lib.ptr(flags),
+                      _material_hints(ebc, i, b), _lib.ptr(vals))
+            continue
         if (b.kind == _lib.KIND_LINEAR and b.material == _lib.MAT_ISOTROPIC and plan.fused_plan(ebc, i) is not None):
             fp = plan.fused_plan(ebc, i)
             flags = _vertex_flags(ebc, mask) if (eliminate and mask is not None) else None
@@ -425,11 +446,22 @@ def _material_hints(ebc, i, b) -> int:
     return _lib.HINT_UNIFORM_POISSON if _poisson_facts(ebc, i)[1] else 0
 
 
+def _use_sweep_kernel(ebc, i, b) -> bool:
+    """feb200_assemble_fused_hex8_sweep (the default) needs one Poisson ratio for the batch: layout (M,), or a material
+    array whose Poisson ratio is the same everywhere (checked once per array, cached).  FEB200_FUSED_IMPL=mma / v4 select
+    the tile kernels instead."""
+    if os.environ.get("FEB200_FUSED_IMPL", "sweep") != "sweep":
+        return False
+    if os.environ.get("FEB200_FUSED", "1") == "0" or ebc.B != 1:
+        return False
+    return b.layout == _lib.LAYOUT_M or _poisson_facts(ebc, i)[1]
+
+
 def _use_tensor_core_kernel(ebc, i, b, fp) -> bool:
     """feb200_assemble_fused_hex8_mma handles materials constant per batch or per element, and per-point fields whose
     Poisson ratio is constant within every element (one check per material array, cached on the collection);
     anything else, or FEB200_FUSED_IMPL=v4, goes to the scalar fused kernel."""
-    if os.environ.get("FEB200_FUSED_IMPL", "mma") != "mma":
+    if os.environ.get("FEB200_FUSED_IMPL", "sweep") == "v4":
         return False
     if b.layout != _lib.LAYOUT_EQM:
         return True

@@ -188,6 +188,32 @@ int feb200_assemble_fused_hex8_mma(feb200_stream s, const feb200_batch* b, const
                                    const uint16_t* slot_rank, const int32_t* nindices, const uint8_t* vertex_flags,
                                    int32_t material_hints, double* values);
 
+/* Streaming variant of the fused hex8 assembly (same outputs as feb200_assemble_fused_hex8_mma up to the summation order,
+ * which here is the plan's visit order; results are bit-reproducible from run to run).  Every warp walks "segments" of
+ * vertex strips: a segment is a list of chunks (4 vertices each; the two chunks c, c+1 are live at step c and own the
+ * 8 panel slots of the warp, chunk c in slots 4*(c&1)..) and a list of visits sorted by step.  A visit is one 16-byte
+ * record {element, slotw, perm, flags}: slotw nibble n = panel slot of local node n (0xF: the node is not in the window),
+ * perm nibble i = i-th in-window node (ascending), flags = count of in-window nodes | (chunks completed by this visit) << 4.
+ * chunk_v / chunk_p0 / chunk_deg: vertex id (-1: empty slot), nindptr[vertex] and its degree, 4 per chunk.
+ * Built by fe_jax/sweep_plan.py for any hex8 connectivity with vertex valence <= 8 and degree <= 32.  Needs one Poisson
+ * ratio for the batch: layout (M,) or FEB200_HINT_UNIFORM_POISSON.  Replaces fea.py:519-572 + :613-660 +
+ * sparse_matrix.py:157-184 like the kernels above. */
+typedef struct {
+    int32_t n_segments;
+    int32_t max_deg;               /* largest vertex degree of the mesh (panel slot = 9 * max_deg doubles) */
+    int32_t reserved[2];
+    const int32_t* seg_visit_ptr;  /* (n_segments+1) */
+    const int32_t* seg_chunk_ptr;  /* (n_segments+1) */
+    const int32_t* visits;         /* (n_visits, 4), 16-byte aligned */
+    const int32_t* chunk_v;        /* (n_chunks, 4) */
+    const int64_t* chunk_p0;       /* (n_chunks, 4) */
+    const int32_t* chunk_deg;      /* (n_chunks, 4) */
+} feb200_sweep_plan;
+int32_t feb200_fused_sweep_warps(int32_t max_deg);   /* workers (warps) per SM the kernel will run with; 0 = does not fit */
+int feb200_assemble_fused_hex8_sweep(feb200_stream s, const feb200_batch* b, const feb200_sweep_plan* plan, const double* x_vd,
+                                     const uint16_t* slot_rank, const int32_t* nindices, const uint8_t* vertex_flags,
+                                     int32_t material_hints, double* values);
+
 /* apply_dirichlet_bcs_lhs on the node-pattern CSR (sparse_matrix.py:157-184). mask: (U*V) 0/1 doubles. */
 int feb200_dirichlet_lhs(feb200_stream s, int64_t V, int32_t U, const int64_t* nindptr, const int32_t* nindices,
                          const double* mask, double* values);

@@ -556,6 +556,57 @@ def test_fused_tensor_core_kernel_matches_scalar_kernel(fj, layout):
     assert torch.equal(out["mma"][0], _assemble_values(token, ebc, maps, u)[0])
 
 
+@pytest.mark.parametrize("layout,keep,dims", [("M", 1.0, (7, 5, 10)), ("EM_nu_uniform", 1.0, (6, 9, 4)),
+                                              ("EQM_nu_uniform", 1.0, (9, 4, 7)), ("M", 0.6, (8, 7, 9)),
+                                              ("EQM_nu_uniform", 0.35, (8, 7, 9)), ("M", 1.0, (1, 1, 1)),
+                                              ("M", 1.0, (3, 2, 70))])
+def test_fused_sweep_kernel_matches_tile_kernel_and_oracle(fj, layout, keep, dims):
+    """feb200_assemble_fused_hex8_sweep (streaming plan, sums kept in warp-private panels; the default for batches with one
+    Poisson ratio) against the oracle and feb200_assemble_fused_hex8_mma, with and without the fused Dirichlet
+    elimination: odd grid sizes (strips of width one), shuffled elements, elements removed at random (vertices with
+    1..8 incident elements or none), strips long enough to be cut into several segments."""
+    from fe_jax.assembly import _assemble_values, _plan
+    Vx, cells = orc.uniform_hex_grid(*dims)
+    rng = np.random.default_rng(17)
+    Vx = Vx + 0.1 / max(dims) * rng.uniform(-1, 1, size=Vx.shape)
+    if keep < 1.0:
+        cells = cells[rng.uniform(size=cells.shape[0]) < keep]
+    cells = cells[rng.permutation(cells.shape[0])]
+    mp = material_params("elastic_isotropic", 3, {"M": (), "EM_nu_uniform": (cells.shape[0],)}.get(layout, (cells.shape[0], 8)),
+                         seed=5)
+    if layout.endswith("nu_uniform"):
+        mp[..., 1] = 0.3
+    spec = [dict(cell="hexahedron", degree=1, qdeg=2, cells=cells, model="elastic_isotropic", mp=mp)]
+    ebc, maps, token, prob, _ = build_pair(fj, Vx, spec)
+    u = torch.zeros(Vx.size, dtype=torch.float64, device="cuda")
+    dofs = np.unique(rng.integers(0, Vx.size, size=max(Vx.size // 7, 1)))
+    mask = torch.zeros(prob.F, dtype=torch.float64, device="cuda")
+    mask[torch.tensor(dofs, device="cuda")] = 1.0
+    vals_g = torch.zeros_like(mask)
+    out = {}
+    for impl in ("sweep", "mma"):
+        os.environ["FEB200_FUSED_IMPL"] = impl
+        try:
+            before = dict(_lib_launches(fj))
+            out[impl] = (_assemble_values(token, ebc, maps, u)[0].clone(),
+                         _assemble_values(token, ebc, maps, u, mask, vals_g, eliminate=True)[0].clone())
+            after = _lib_launches(fj)
+            name = "feb200_assemble_fused_hex8_" + impl
+            assert after.get(name, 0) - before.get(name, 0) == 2, "the requested kernel did not run"
+        finally:
+            os.environ.pop("FEB200_FUSED_IMPL", None)
+    assert _plan(ebc, maps).sweep_plan(ebc, 0).stats["n_segments"] >= 1
+    d_o, r_o, c_o = prob.jacobian_wo_dirichlet(np.zeros(Vx.size))
+    dw_o = orc.apply_dirichlet_bcs_lhs(d_o, r_o, c_o, dofs)
+    for impl in ("sweep", "mma"):
+        assert rel_err(out[impl][0], d_o) <= ASM_RTOL and rel_err(out[impl][1], dw_o) <= ASM_RTOL, impl
+    if keep == 1.0:
+        assert np.array_equal(np_(out["sweep"][1]) == 1.0, dw_o == 1.0) and np.array_equal(np_(out["sweep"][1]) == 0.0, dw_o == 0.0)
+    assert rel_err(out["sweep"][0], out["mma"][0].cpu().numpy()) <= 1e-13
+    # bit-reproducible across launches (the summation order is the plan's, not the scheduler's)
+    assert torch.equal(out["sweep"][0], _assemble_values(token, ebc, maps, u)[0])
+
+
 def _lib_launches(fj):
     from fe_jax import _lib
     return dict(_lib.launches_by_name)
