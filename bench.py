@@ -323,9 +323,11 @@ def main():
     sweep = plan.sweep_plan(ebc, 0) if (not hyper and _use_sweep_kernel(ebc, 0, bstruct)) else None
     use_mma = sweep is None and fused is not None and _use_tensor_core_kernel(ebc, 0, bstruct, fused)
     if sweep is not None:
+        from fe_jax.assembly import _block_flags
+        bflags = _block_flags(ebc, pat, mask)
         kernels["assemble_fused_hex8"] = lambda: _lib.call(
             "feb200_assemble_fused_hex8_sweep", bstruct, sweep.struct, _lib.ptr(ebc._vertices), _lib.ptr(plan.slot_rank[0]),
-            _lib.ptr(pat.nindices), _lib.ptr(vflags), _material_hints(ebc, 0, bstruct), _lib.ptr(J_vals))
+            _lib.ptr(bflags), _material_hints(ebc, 0, bstruct), _lib.ptr(J_vals))
     elif use_mma:
         kernels["assemble_fused_hex8"] = lambda: _lib.call(
             "feb200_assemble_fused_hex8_mma", bstruct, fused.struct, _lib.ptr(ebc._vertices), _lib.ptr(plan.slot_rank[0]),

@@ -46,8 +46,7 @@ class FusedPlan(Structure):
 
 class SweepPlan(Structure):
     _fields_ = [("n_segments", c_int32), ("max_deg", c_int32), ("reserved0", c_int32), ("reserved1", c_int32),
-                ("seg_visit_ptr", c_void_p), ("seg_chunk_ptr", c_void_p), ("visits", c_void_p),
-                ("chunk_v", c_void_p), ("chunk_p0", c_void_p), ("chunk_deg", c_void_p)]
+                ("seg_visit_ptr", c_void_p), ("seg_chunk_ptr", c_void_p), ("visits", c_void_p), ("chunk_rec", c_void_p)]
 
 
 class CGState(Structure):
@@ -87,7 +86,8 @@ SIGNATURES = {
     "feb200_fused_mma_smem_bytes": (_SZ, [_I32, _I32, _I32]),
     "feb200_assemble_fused_hex8_mma": (c_int32, [_P, POINTER(Batch), POINTER(FusedPlan), _P, _P, _P, _P, _I32, _P]),
     "feb200_fused_sweep_warps": (c_int32, [_I32]),
-    "feb200_assemble_fused_hex8_sweep": (c_int32, [_P, POINTER(Batch), POINTER(SweepPlan), _P, _P, _P, _P, _I32, _P]),
+    "feb200_sweep_block_flags": (c_int32, [_P, _I64, _P, _P, _P, _P]),
+    "feb200_assemble_fused_hex8_sweep": (c_int32, [_P, POINTER(Batch), POINTER(SweepPlan), _P, _P, _P, _I32, _P]),
     "feb200_dirichlet_lhs": (c_int32, [_P, _I64, _I32, _P, _P, _P, _P]),
     "feb200_dirichlet_lhs_coo": (c_int32, [_P, _I64, _P, _P, _P, _P, _P]),
     "feb200_csr_diagonal": (c_int32, [_P, _I64, _I32, _P, _P, _P, _P]),

@@ -395,10 +395,9 @@ def _assemble_values(element_residual_func, ebc, assembly_map_b, u, mask=None, v
         # Streaming kernel when the batch has one Poisson ratio, else the tile kernels.
         if (b.kind == _lib.KIND_LINEAR and b.material == _lib.MAT_ISOTROPIC and _use_sweep_kernel(ebc, i, b)
                 and plan.sweep_plan(ebc, i) is not None):
-            flags = _vertex_flags(ebc, mask) if (eliminate and mask is not None) else None
+            flags = _block_flags(ebc, pat, mask) if (eliminate and mask is not None) else None
             _lib.call("feb200_assemble_fused_hex8_sweep", b, plan.sweep_plan(ebc, i).struct, _lib.ptr(ebc._vertices),
-                      _lib.ptr(plan.slot_rank[i]), _lib.ptr(pat.nindices), _lib.ptr(flags),
-                      _material_hints(ebc, i, b), _lib.ptr(vals))
+                      _lib.ptr(plan.slot_rank[i]), _lib.ptr(flags), _material_hints(ebc, i, b), _lib.ptr(vals))
             continue
         if (b.kind == _lib.KIND_LINEAR and b.material == _lib.MAT_ISOTROPIC and plan.fused_plan(ebc, i) is not None):
             fp = plan.fused_plan(ebc, i)
@@ -484,6 +483,22 @@ def _vertex_flags(ebc, mask):
     except AttributeError:
         pass
     return flags
+
+
+def _block_flags(ebc, pat, mask):
+    """(V, 32) uint8 Dirichlet flags per CSR block row (input of the streaming kernel's fused elimination), derived from
+    the per-vertex flags and the node pattern; cached on the mask tensor like `_vertex_flags`."""
+    hit = getattr(mask, "_feb200_bflags", None)
+    if hit is not None and hit[0] == mask._version and hit[1] is pat:
+        return hit[2]
+    vf = _vertex_flags(ebc, mask)
+    out = torch.empty((pat.V, 32), dtype=torch.uint8, device=mask.device)
+    _lib.call("feb200_sweep_block_flags", pat.V, _lib.ptr(pat.nindptr), _lib.ptr(pat.nindices), _lib.ptr(vf), _lib.ptr(out))
+    try:
+        mask._feb200_bflags = (mask._version, pat, out)
+    except AttributeError:
+        pass
+    return out
 
 
 def calculate_jacobian_wo_dirichlet(element_residual_func, ebc: ElementBatchCollection, assembly_map_b, u_f,

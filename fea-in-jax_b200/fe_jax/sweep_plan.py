@@ -11,7 +11,8 @@ c is complete after the last visit of step c.  Works for any hex8 connectivity w
 <= 32 (elements whose in-segment nodes spread over non-adjacent chunks are simply visited more than once); returns None
 when the mesh is not eligible (the caller then uses the tile kernel or the two-pass path).
 
-Record layout (include/feb200.h, feb200_sweep_plan): visits (n, 4) int32 = element, slotw, perm, flags.
+Record layout (include/feb200.h, feb200_sweep_plan): visits (n, 12) int32 = element, slotw, perm, flags, the element's 8
+vertex ids; chunk records (n, 16) int32 = v[4], deg[4], p0[4] as int64.
 """
 from __future__ import annotations
 
@@ -78,7 +79,19 @@ def _perm_lut(device):
 class SweepPlan:
     def __init__(self, struct, keep, stats):
         self.struct, self._keep, self.stats = struct, keep, stats
-        (self.seg_visit_ptr, self.seg_chunk_ptr, self.visits, self.chunk_v, self.chunk_p0, self.chunk_deg) = keep
+        (self.seg_visit_ptr, self.seg_chunk_ptr, self.visits, self.chunk_rec) = keep
+
+    @property
+    def chunk_v(self):
+        return self.chunk_rec[:, 0:4]
+
+    @property
+    def chunk_deg(self):
+        return self.chunk_rec[:, 4:8]
+
+    @property
+    def chunk_p0(self):
+        return self.chunk_rec[:, 8:16].contiguous().view(torch.int64)
 
 
 def build_sweep_plan(vertices: torch.Tensor, conn32: torch.Tensor, row_ind: torch.Tensor, col_ind: torch.Tensor,
@@ -194,13 +207,15 @@ def build_sweep_plan(vertices: torch.Tensor, conn32: torch.Tensor, row_ind: torc
     if int(nret.max().item()) > 15 or bool((v_step[first_of_seg] != 0).any().item()):
         return None
     flags = cnt | (nret << 4)
-    visits = torch.stack([v_elem, slotw, perm, flags], dim=1)
-    visits = torch.where(visits >= (1 << 31), visits - (1 << 32), visits).to(torch.int32).contiguous()
+    head = torch.stack([v_elem, slotw, perm, flags], dim=1)
+    head = torch.where(head >= (1 << 31), head - (1 << 32), head).to(torch.int32)
+    visits = torch.cat([head, conn32[v_elem].to(torch.int32)], dim=1).contiguous()
     seg_visit_ptr = torch.searchsorted(v_seg.contiguous(), torch.arange(n_seg + 1, device=dev)).to(torch.int32)
     if bool((seg_visit_ptr[1:] == seg_visit_ptr[:-1]).any().item()):
         return None                                          # every segment has visits (its vertices have elements)
-    keep = [seg_visit_ptr.contiguous(), seg_chunk_ptr.to(torch.int32).contiguous(), visits, chunk_v.reshape(-1, 4),
-            chunk_p0.reshape(-1, 4), chunk_deg.reshape(-1, 4)]
+    chunk_rec = torch.cat([chunk_v.reshape(-1, 4), chunk_deg.reshape(-1, 4),
+                           chunk_p0.reshape(-1, 4).contiguous().view(torch.int32).reshape(-1, 8)], dim=1).contiguous()
+    keep = [seg_visit_ptr.contiguous(), seg_chunk_ptr.to(torch.int32).contiguous(), visits, chunk_rec]
     stats = dict(n_segments=n_seg, n_chunks=n_chunks, n_visits=n_vis, n_strips=n_strips, sweep_axis=s_ax,
                  visits_per_element=n_vis / E, max_deg=max_deg,
                  row_tiles_per_vertex=float(((3 * cnt + 7) // 8).sum().item()) / max(n_act, 1))
@@ -209,6 +224,5 @@ def build_sweep_plan(vertices: torch.Tensor, conn32: torch.Tensor, row_ind: torc
         if int(_lib.load().feb200_fused_sweep_warps(max_deg)) < 1:
             return None
         struct = _lib.SweepPlan(n_segments=n_seg, max_deg=max_deg, seg_visit_ptr=_lib.ptr(keep[0]),
-                                seg_chunk_ptr=_lib.ptr(keep[1]), visits=_lib.ptr(keep[2]), chunk_v=_lib.ptr(keep[3]),
-                                chunk_p0=_lib.ptr(keep[4]), chunk_deg=_lib.ptr(keep[5]))
+                                seg_chunk_ptr=_lib.ptr(keep[1]), visits=_lib.ptr(keep[2]), chunk_rec=_lib.ptr(keep[3]))
     return SweepPlan(struct, keep, stats)

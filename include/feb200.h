@@ -191,28 +191,32 @@ int feb200_assemble_fused_hex8_mma(feb200_stream s, const feb200_batch* b, const
 /* Streaming variant of the fused hex8 assembly (same outputs as feb200_assemble_fused_hex8_mma up to the summation order,
  * which here is the plan's visit order; results are bit-reproducible from run to run).  Every warp walks "segments" of
  * vertex strips: a segment is a list of chunks (4 vertices each; the two chunks c, c+1 are live at step c and own the
- * 8 panel slots of the warp, chunk c in slots 4*(c&1)..) and a list of visits sorted by step.  A visit is one 16-byte
- * record {element, slotw, perm, flags}: slotw nibble n = panel slot of local node n (0xF: the node is not in the window),
- * perm nibble i = i-th in-window node (ascending), flags = count of in-window nodes | (chunks completed by this visit) << 4.
- * chunk_v / chunk_p0 / chunk_deg: vertex id (-1: empty slot), nindptr[vertex] and its degree, 4 per chunk.
+ * 8 panel slots of the warp, chunk c in slots 4*(c&1)..) and a list of visits sorted by step.  A visit is one 48-byte
+ * record of 12 int32 {element, slotw, perm, flags, conn[8]}: slotw nibble n = panel slot of local node n (0xF: the node is
+ * not in the window), perm nibble i = i-th in-window node (ascending), flags = count of in-window nodes | (chunks
+ * completed by this visit) << 4, conn = the element's vertex ids.  A chunk record is 64 bytes: int32 v[4] (vertex id,
+ * -1: empty slot), int32 deg[4] (its degree), int64 p0[4] (nindptr[vertex]).
  * Built by fe_jax/sweep_plan.py for any hex8 connectivity with vertex valence <= 8 and degree <= 32.  Needs one Poisson
- * ratio for the batch: layout (M,) or FEB200_HINT_UNIFORM_POISSON.  Replaces fea.py:519-572 + :613-660 +
- * sparse_matrix.py:157-184 like the kernels above. */
+ * ratio for the batch: layout (M,) or FEB200_HINT_UNIFORM_POISSON.  block_flags != NULL fuses apply_dirichlet_bcs_lhs:
+ * 32 bytes per vertex from feb200_sweep_block_flags (byte r = flags of CSR block r of the vertex row).  Replaces
+ * fea.py:519-572 + :613-660 + sparse_matrix.py:157-184 like the kernels above. */
 typedef struct {
     int32_t n_segments;
     int32_t max_deg;               /* largest vertex degree of the mesh (panel slot = 9 * max_deg doubles) */
     int32_t reserved[2];
     const int32_t* seg_visit_ptr;  /* (n_segments+1) */
     const int32_t* seg_chunk_ptr;  /* (n_segments+1) */
-    const int32_t* visits;         /* (n_visits, 4), 16-byte aligned */
-    const int32_t* chunk_v;        /* (n_chunks, 4) */
-    const int64_t* chunk_p0;       /* (n_chunks, 4) */
-    const int32_t* chunk_deg;      /* (n_chunks, 4) */
+    const int32_t* visits;         /* (n_visits, 12), 16-byte aligned */
+    const int32_t* chunk_rec;      /* (n_chunks, 16), 16-byte aligned */
 } feb200_sweep_plan;
 int32_t feb200_fused_sweep_warps(int32_t max_deg);   /* workers (warps) per SM the kernel will run with; 0 = does not fit */
+/* block_flags[32*v + r] = (constrained components of neighbour r of v) | (neighbour == v) << 3 | (constrained
+ * components of v) << 4, from the per-vertex flags (bit j: DoF 3*v+j constrained) and the node pattern. */
+int feb200_sweep_block_flags(feb200_stream s, int64_t V, const int64_t* nindptr, const int32_t* nindices,
+                             const uint8_t* vertex_flags, uint8_t* block_flags);
 int feb200_assemble_fused_hex8_sweep(feb200_stream s, const feb200_batch* b, const feb200_sweep_plan* plan, const double* x_vd,
-                                     const uint16_t* slot_rank, const int32_t* nindices, const uint8_t* vertex_flags,
-                                     int32_t material_hints, double* values);
+                                     const uint16_t* slot_rank, const uint8_t* block_flags, int32_t material_hints,
+                                     double* values);
 
 /* apply_dirichlet_bcs_lhs on the node-pattern CSR (sparse_matrix.py:157-184). mask: (U*V) 0/1 doubles. */
 int feb200_dirichlet_lhs(feb200_stream s, int64_t V, int32_t U, const int64_t* nindptr, const int32_t* nindices,

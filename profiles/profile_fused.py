@@ -14,8 +14,12 @@ Vx, cells, mp = make_problem(n, n, layout)
 fe = fj.FiniteElementType(fj.CellType.hexahedron, fj.ElementFamily.P, 1, fj.LagrangeVariant.equispaced, fj.QuadratureType.default, 2)
 batch = fj.ElementBatch(fe_type=fe, n_dofs_per_basis=3, connectivity_en=cells, constitutive_model=fj.elastic_isotropic, material_params=mp)
 ebc = fj.batch_to_collection(Vx, [batch]); maps = [fj.mesh_to_sparse_assembly_map(Vx.shape[0], cells)]
-plan = _plan(ebc, maps); fp = plan.fused_plan(ebc, 0)
-print("plan stats", fp.stats, "tn_cap", fp.tn_cap)
+plan = _plan(ebc, maps)
+if os.environ.get("FEB200_FUSED_IMPL", "sweep") == "sweep":
+    print("sweep plan stats", plan.sweep_plan(ebc, 0).stats)
+else:
+    fp = plan.fused_plan(ebc, 0)
+    print("plan stats", fp.stats, "tn_cap", fp.tn_cap)
 u = torch.zeros(3 * Vx.shape[0], dtype=torch.float64, device="cuda")
 mask = torch.zeros_like(u); mask[:300] = 1.0
 out = torch.empty(plan.pattern.nnz, dtype=torch.float64, device="cuda")

@@ -553,7 +553,11 @@ def test_fused_tensor_core_kernel_matches_scalar_kernel(fj, layout):
         assert rel_err(out[impl][0], d_o) <= ASM_RTOL and rel_err(out[impl][1], dw_o) <= ASM_RTOL
     assert rel_err(out["mma"][0], out["v4"][0].cpu().numpy()) <= 1e-13
     # bit-reproducible across launches
-    assert torch.equal(out["mma"][0], _assemble_values(token, ebc, maps, u)[0])
+    os.environ["FEB200_FUSED_IMPL"] = "mma"
+    try:
+        assert torch.equal(out["mma"][0], _assemble_values(token, ebc, maps, u)[0])
+    finally:
+        os.environ.pop("FEB200_FUSED_IMPL", None)
 
 
 @pytest.mark.parametrize("layout,keep,dims", [("M", 1.0, (7, 5, 10)), ("EM_nu_uniform", 1.0, (6, 9, 4)),

@@ -51,7 +51,9 @@ def test_sweep_plan_data_flow_reproduces_oracle_jacobian(dims, shuffle, seg_chun
     V, E = Vx.shape[0], cells.shape[0]
     plan, lists, nindptr, ri = _build(Vx, cells, seg_chunks)
     assert plan is not None
-    seg_vptr, seg_cptr, visits, chunk_v, chunk_p0, chunk_deg = (t.numpy() for t in plan._keep)
+    seg_vptr, seg_cptr, visits = (t.numpy() for t in plan._keep[:3])
+    chunk_v, chunk_p0, chunk_deg = plan.chunk_v.numpy(), plan.chunk_p0.numpy(), plan.chunk_deg.numpy()
+    assert visits.shape[1] == 12 and np.array_equal(visits[:, 4:], cells[visits[:, 0]])   # the records carry the vertex ids
     max_deg = plan.stats["max_deg"]
     # every vertex in exactly one chunk slot, with its pattern offset and degree
     live = chunk_v[chunk_v >= 0]
@@ -83,7 +85,7 @@ def test_sweep_plan_data_flow_reproduces_oracle_jacobian(dims, shuffle, seg_chun
         c0, c1 = seg_cptr[seg], seg_cptr[seg + 1]
         c_next = c0
         for vi in range(seg_vptr[seg], seg_vptr[seg + 1]):
-            e, slotw, perm, flags = (int(x) & 0xFFFFFFFF for x in visits[vi])
+            e, slotw, perm, flags = (int(x) & 0xFFFFFFFF for x in visits[vi, :4])
             cnt, nret = flags & 0xF, (flags >> 4) & 0xF
             Gm = g[e].transpose(1, 2, 0).reshape(24, 8)              # rows (n, d), columns q
             S = (Gm * (detJ[e] * Wr * mu_q[e])) @ Gm.T               # the material enters through the weights
@@ -92,10 +94,10 @@ def test_sweep_plan_data_flow_reproduces_oracle_jacobian(dims, shuffle, seg_chun
             step = c_next - c0
             for mt in range((3 * cnt + 7) // 8):                     # the kernel's row tiles
                 for gid in range(8):
-                    R = 8 * mt + gid
-                    s, d = R // 3, R % 3
-                    if s >= cnt:
+                    R = 8 * mt + gid                                 # component-major over the in-window nodes
+                    if R >= 3 * cnt:
                         continue
+                    d, s = R // cnt, R % cnt
                     na = (perm >> (4 * s)) & 7
                     slot = (slotw >> (4 * na)) & 0xF
                     a = cells[e, na]
