@@ -28,10 +28,38 @@
 #include "hex8_mma.cuh"
 
 #ifndef FEB_SW_MAXWARPS
-#define FEB_SW_MAXWARPS 9
+#define FEB_SW_MAXWARPS 8            /* measured at 200^3: 7 / 8 / 9 warps (168 registers) = 13.0 / 11.9 / 12.7 ms */
 #endif
 #ifndef FEB_SW_DMAJOR
-#define FEB_SW_DMAJOR 1            /* rows of a visit: 1 = component-major over the in-window nodes, 0 = node-major */
+#define FEB_SW_DMAJOR 0            /* rows of a visit: 1 = component-major over the in-window nodes, 0 = node-major */
+#endif
+#ifndef FEB_SW_ROWS6
+#define FEB_SW_ROWS6 1             /* 1 = a row tile holds two nodes (rows 0-2 and 4-6; rows 3 and 7 stay empty): the 16 lanes of a
+                                      half-warp then touch ONE node's three panel rows and the accumulator loads / stores are free of
+                                      bank conflicts (with three nodes per tile every such access was a 2-way conflict, 70 of 330
+                                      wavefronts per vertex); costs one more row tile for the elements with all 8 nodes in the window */
+#endif
+#ifndef FEB_SW_DPHI_REGS
+#define FEB_SW_DPHI_REGS 1         /* 1 = every lane keeps the basis table of its quadrature point in registers */
+#endif
+// Panel layout: value (rank r, row component d, column component k) of slot s at  sbase[s] + r * BS + d * DS + k * KK.
+// COLS: local node of accumulator column 0..7 (a lane holds columns 2 * tig and 2 * tig + 1 of every column tile);
+// PAD: start of slot s modulo 16 doubles (-1: wherever the previous slot ends) -- both chosen so that the 16 lanes of a half-warp (4 rows x 4 column
+// pairs) spread over the 16 eight-byte banks on structured grids (profiles/r02_panel_layout_search.txt).
+#ifndef FEB_SW_BS
+#define FEB_SW_BS 9
+#endif
+#ifndef FEB_SW_DS
+#define FEB_SW_DS 3
+#endif
+#ifndef FEB_SW_KK
+#define FEB_SW_KK 1
+#endif
+#ifndef FEB_SW_COLS
+#define FEB_SW_COLS {0, 1, 2, 3, 4, 5, 6, 7}
+#endif
+#ifndef FEB_SW_PAD
+#define FEB_SW_PAD {-1, -1, -1, -1, -1, -1, -1, -1}
 #endif
 
 namespace feb {
@@ -45,14 +73,24 @@ constexpr int SW_REC = 12;     // int32 per visit record: element, slotw, perm, 
 constexpr size_t SW_SMEM_MAX = 227 * 1024;
 
 struct SwSmem {
-    int warps, ss;
+    int warps, ss, panel_doubles;
+    int sbase[8];                  // doubles: start of panel slot s within the warp's panel area
     int off_rk, off_rec, off_info, off_flg, off_eq, off_x, off_g, off_panel;
     size_t off_warps, per_warp, total;
 };
 static inline SwSmem sweep_layout(int max_deg) {
     SwSmem L;
-    L.ss = 9 * max_deg;                                  // doubles per panel slot: [rank][3][3]
-    size_t o = (size_t)(8 * SW_DPHI + 8) * 8;            // basis table + weights (shared by the block)
+    L.ss = FEB_SW_BS * max_deg;                          // doubles per panel slot: [rank] BS
+    const int pad[8] = FEB_SW_PAD;
+    int panel_doubles = 0;
+    for (int sl = 0; sl < SW_SLOTS; ++sl) {
+        int start = panel_doubles;
+        if (pad[sl] >= 0)
+            while ((start & 15) != (pad[sl] & 15)) ++start;
+        L.sbase[sl] = start;
+        panel_doubles = start + L.ss;
+    }
+    size_t o = (size_t)(8 * SW_DPHI + 8) * 8 + 8 * 4;    // basis table + weights + slot starts (shared by the block)
     L.off_warps = (o + 15) & ~(size_t)15;
     int w = 0;
     L.off_rk = w;    w += 2 * 4 * 64 * 2;                // [2][4 elements][8][8] uint16 slot ranks (double buffered)
@@ -62,7 +100,8 @@ static inline SwSmem sweep_layout(int max_deg) {
     L.off_eq = w;    w += 4 * 8 * 8;                     // Young's modulus per (element, point) of the next group
     L.off_x = w;     w += 4 * SW_XS * 8;                 // coordinates of the next group
     L.off_g = w;     w += 4 * SW_EL * 8;                 // fragment buffers of the current group
-    L.off_panel = w; w += SW_SLOTS * L.ss * 8;
+    L.panel_doubles = panel_doubles;
+    L.off_panel = w; w += panel_doubles * 8;
     L.per_warp = ((size_t)w + 15) & ~(size_t)15;
     int warps = (int)((SW_SMEM_MAX - L.off_warps) / L.per_warp);
     if (warps > FEB_SW_MAXWARPS) warps = FEB_SW_MAXWARPS;
@@ -98,7 +137,7 @@ __device__ __forceinline__ int sw_grow(int n, int d) { return 8 * d + (((n < 4 ?
 template <int NMT>
 __device__ __forceinline__ void sweep_rows(const double* __restrict__ Ge, const double (&Bf)[3][2], double w0, double w1,
                                            const uint16_t* __restrict__ rk, unsigned slotw, unsigned perm, int cnt,
-                                           double* __restrict__ panel, int ss, int gid, int tig) {
+                                           double* __restrict__ panel, const int* __restrict__ sbase, int gid, int tig, int node0, int node1) {
     double A[NMT][2];
     double* base0[NMT];
     double* base1[NMT];
@@ -107,7 +146,10 @@ __device__ __forceinline__ void sweep_rows(const double* __restrict__ Ge, const 
 #pragma unroll
     for (int mt = 0; mt < NMT; ++mt) {
         const int R = 8 * mt + gid;
-#if FEB_SW_DMAJOR
+#if FEB_SW_ROWS6
+        const int s = 2 * mt + (gid >> 2), d = gid & 3;
+        valid[mt] = d < 3 && s < cnt;
+#elif FEB_SW_DMAJOR
         const int d = (R >= cnt ? 1 : 0) + (R >= 2 * cnt ? 1 : 0), s = R - d * cnt;
         valid[mt] = R < 3 * cnt;
 #else
@@ -117,10 +159,9 @@ __device__ __forceinline__ void sweep_rows(const double* __restrict__ Ge, const 
         const int na = valid[mt] ? (int)((perm >> (4 * s)) & 7u) : 0;
         const int dd = valid[mt] ? d : 0;
         const int slot = (int)((slotw >> (4 * na)) & 7u);
-        const unsigned rk2 = *reinterpret_cast<const unsigned*>(rk + na * 8 + 2 * tig);
-        double* pb = panel + slot * ss + dd * 3;
-        base0[mt] = pb + (rk2 & 0xffffu) * 9u;
-        base1[mt] = pb + (rk2 >> 16) * 9u;
+        double* pb = panel + sbase[slot] + dd * FEB_SW_DS;
+        base0[mt] = pb + (unsigned)rk[na * 8 + node0] * (unsigned)FEB_SW_BS;
+        base1[mt] = pb + (unsigned)rk[na * 8 + node1] * (unsigned)FEB_SW_BS;
         const int gr = sw_grow(na, dd) * 4 + tig;
         const double g0 = Ge[gr], g1 = Ge[SW_KS + gr];
         A[mt][0] = valid[mt] ? w0 * g0 : 0.0;
@@ -130,8 +171,8 @@ __device__ __forceinline__ void sweep_rows(const double* __restrict__ Ge, const 
             C[mt][nt][0] = 0.0;
             C[mt][nt][1] = 0.0;
             if (valid[mt]) {
-                C[mt][nt][0] = base0[mt][nt];
-                C[mt][nt][1] = base1[mt][nt];
+                C[mt][nt][0] = base0[mt][nt * FEB_SW_KK];
+                C[mt][nt][1] = base1[mt][nt * FEB_SW_KK];
             }
         }
     }
@@ -148,8 +189,8 @@ __device__ __forceinline__ void sweep_rows(const double* __restrict__ Ge, const 
         if (valid[mt]) {
 #pragma unroll
             for (int nt = 0; nt < 3; ++nt) {
-                base0[mt][nt] = C[mt][nt][0];
-                base1[mt][nt] = C[mt][nt][1];
+                base0[mt][nt * FEB_SW_KK] = C[mt][nt][0];
+                base1[mt][nt * FEB_SW_KK] = C[mt][nt][1];
             }
         }
 }
@@ -166,6 +207,7 @@ k_fused_hex8_sweep(feb200_batch b, feb200_sweep_plan plan, SwSmem L, const doubl
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* s_dphi = reinterpret_cast<double*>(smem_raw);                    // [q] DPHI : [n][3]
     double* s_w = s_dphi + 8 * SW_DPHI;                                      // [q]
+    int* s_sbase = reinterpret_cast<int*>(s_w + 8);                          // [slot] start of the slot's panel (doubles)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gid = lane >> 2, tig = lane & 3;
     unsigned char* mine = smem_raw + L.off_warps + (size_t)warp * L.per_warp;
@@ -176,12 +218,24 @@ k_fused_hex8_sweep(feb200_batch b, feb200_sweep_plan plan, SwSmem L, const doubl
     double* eqbuf = reinterpret_cast<double*>(mine + L.off_eq);              // [4][8]
     double* xbuf = reinterpret_cast<double*>(mine + L.off_x);                // [4] XS
     double* Gw = reinterpret_cast<double*>(mine + L.off_g);                  // [4] EL : [ks] KS : [row][4 points], weights at 96
-    double* panel = reinterpret_cast<double*>(mine + L.off_panel);           // [slot] ss : [rank][3][3]
-    const int ss = L.ss;
+    double* panel = reinterpret_cast<double*>(mine + L.off_panel);           // slot s at sbase[s] : [rank] BS : (d, k) at d * DS + k * KK
+    constexpr int cols[8] = FEB_SW_COLS;
+    int node0 = 0, node1 = 0, bnode = 0;                                     // local nodes of this lane's two accumulator columns / its B column
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        if (c == 2 * tig) node0 = cols[c];
+        if (c == 2 * tig + 1) node1 = cols[c];
+        if (c == gid) bnode = cols[c];
+    }
 
     for (int i = tid; i < 8 * 24; i += blockDim.x) s_dphi[(i / 24) * SW_DPHI + (i % 24)] = b.dphi[i];
-    if (tid < 8) s_w[tid] = b.W[tid];
-    for (int i = lane; i < SW_SLOTS * ss; i += 32) panel[i] = 0.0;
+    if (tid < 8) { s_w[tid] = b.W[tid]; s_sbase[tid] = L.sbase[tid]; }
+    for (int i = lane; i < L.panel_doubles; i += 32) panel[i] = 0.0;
+#if FEB_SW_DPHI_REGS
+    double dq[24];                                       // basis table of this lane's quadrature point
+#pragma unroll
+    for (int i = 0; i < 24; ++i) dq[i] = b.dphi[(lane & 7) * 24 + i];
+#endif
     double u_lam, u_mu;
     isotropic_lame<3>(b.mp, u_lam, u_mu);
     const double half_inv = 0.5 / (1.0 + b.mp[1]);      // mu = E * half_inv
@@ -261,7 +315,11 @@ k_fused_hex8_sweep(feb200_batch b, feb200_sweep_plan plan, SwSmem L, const doubl
             // ---- geometry of the group: lane = (element jj, point qq)
             if (rg[jj * SW_REC] >= 0) {
                 double gr[24];
+#if FEB_SW_DPHI_REGS
+                const double dt = hex8_gradients_rd(xbuf + jj * SW_XS, dq, gr);
+#else
                 const double dt = hex8_gradients(xbuf + jj * SW_XS, s_dphi + qq * SW_DPHI, gr);
+#endif
                 double* dst = Gw + jj * SW_EL + (qq >> 2) * SW_KS + (qq & 3);
 #pragma unroll
                 for (int n = 0; n < 8; ++n)
@@ -289,13 +347,20 @@ k_fused_hex8_sweep(feb200_batch b, feb200_sweep_plan plan, SwSmem L, const doubl
                 double Bf[3][2];
 #pragma unroll
                 for (int nt = 0; nt < 3; ++nt) {
-                    Bf[nt][0] = Ge[sw_grow(gid, nt) * 4 + tig];
-                    Bf[nt][1] = Ge[SW_KS + sw_grow(gid, nt) * 4 + tig];
+                    Bf[nt][0] = Ge[sw_grow(bnode, nt) * 4 + tig];
+                    Bf[nt][1] = Ge[SW_KS + sw_grow(bnode, nt) * 4 + tig];
                 }
                 const double w0 = Ge[96 + tig], w1 = Ge[SW_KS + 96 + tig];
-                if (cnt > 5) sweep_rows<3>(Ge, Bf, w0, w1, rk, slotw, perm, cnt, panel, ss, gid, tig);
-                else if (cnt > 2) sweep_rows<2>(Ge, Bf, w0, w1, rk, slotw, perm, cnt, panel, ss, gid, tig);
-                else sweep_rows<1>(Ge, Bf, w0, w1, rk, slotw, perm, cnt, panel, ss, gid, tig);
+#if FEB_SW_ROWS6
+                if (cnt > 6) sweep_rows<4>(Ge, Bf, w0, w1, rk, slotw, perm, cnt, panel, s_sbase, gid, tig, node0, node1);
+                else if (cnt > 4) sweep_rows<3>(Ge, Bf, w0, w1, rk, slotw, perm, cnt, panel, s_sbase, gid, tig, node0, node1);
+                else if (cnt > 2) sweep_rows<2>(Ge, Bf, w0, w1, rk, slotw, perm, cnt, panel, s_sbase, gid, tig, node0, node1);
+                else sweep_rows<1>(Ge, Bf, w0, w1, rk, slotw, perm, cnt, panel, s_sbase, gid, tig, node0, node1);
+#else
+                if (cnt > 5) sweep_rows<3>(Ge, Bf, w0, w1, rk, slotw, perm, cnt, panel, s_sbase, gid, tig, node0, node1);
+                else if (cnt > 2) sweep_rows<2>(Ge, Bf, w0, w1, rk, slotw, perm, cnt, panel, s_sbase, gid, tig, node0, node1);
+                else sweep_rows<1>(Ge, Bf, w0, w1, rk, slotw, perm, cnt, panel, s_sbase, gid, tig, node0, node1);
+#endif
                 __syncwarp();
                 // ---- chunks completed by this visit: combine, eliminate, store, clear
                 for (int nret = (hd.w >> 4) & 0xf; nret > 0; --nret) {
@@ -309,10 +374,15 @@ k_fused_hex8_sweep(feb200_batch b, feb200_sweep_plan plan, SwSmem L, const doubl
                         const int deg = ci[4 + s];
                         if (v >= 0 && lane < deg) {
                             const int64_t p0 = *reinterpret_cast<const int64_t*>(ci + 8 + 2 * s);
-                            double* src = panel + (4 * (cr & 1) + s) * ss + lane * 9;
+                            double* src = panel + s_sbase[4 * (cr & 1) + s] + lane * FEB_SW_BS;
                             double S[9], K[9];
 #pragma unroll
-                            for (int c = 0; c < 9; ++c) { S[c] = src[c]; src[c] = 0.0; }
+                            for (int d = 0; d < 3; ++d)
+#pragma unroll
+                                for (int kk = 0; kk < 3; ++kk) {
+                                    S[d * 3 + kk] = src[d * FEB_SW_DS + kk * FEB_SW_KK];
+                                    src[d * FEB_SW_DS + kk * FEB_SW_KK] = 0.0;
+                                }
                             const double tr = u_mu * (S[0] + S[4] + S[8]);
 #pragma unroll
                             for (int d = 0; d < 3; ++d)

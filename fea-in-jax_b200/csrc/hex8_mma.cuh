@@ -48,4 +48,33 @@ __device__ __forceinline__ double hex8_gradients(const double* __restrict__ xe, 
     return dt;
 }
 
+// The same with the point's basis table held in registers (dq[n*3+p]).
+__device__ __forceinline__ double hex8_gradients_rd(const double* __restrict__ xe, const double (&dq)[24], double (&g)[24]) {
+    const double2* x2 = reinterpret_cast<const double2*>(xe);
+    double J[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+        const double2 xa = x2[3 * h], xb = x2[3 * h + 1], xc = x2[3 * h + 2];
+        const double x[6] = {xa.x, xa.y, xb.x, xb.y, xc.x, xc.y};
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int pp = 0; pp < 3; ++pp)
+#pragma unroll
+                for (int dd = 0; dd < 3; ++dd) J[pp][dd] += x[3 * m + dd] * dq[6 * h + 3 * m + pp];
+    }
+    double Ji[3][3];
+    const double dt = inverse(J, Ji);
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+        for (int dd = 0; dd < 3; ++dd) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int pp = 0; pp < 3; ++pp) sacc += Ji[dd][pp] * dq[n * 3 + pp];
+            g[n * 3 + dd] = sacc;
+        }
+    return dt;
+}
+
 }  // namespace feb

@@ -92,12 +92,11 @@ def test_sweep_plan_data_flow_reproduces_oracle_jacobian(dims, shuffle, seg_chun
             in_window = [n for n in range(8) if (slotw >> (4 * n)) & 0xF != 0xF]
             assert cnt == len(in_window) >= 1 and [(perm >> (4 * i)) & 7 for i in range(cnt)] == in_window
             step = c_next - c0
-            for mt in range((3 * cnt + 7) // 8):                     # the kernel's row tiles
-                for gid in range(8):
-                    R = 8 * mt + gid                                 # component-major over the in-window nodes
-                    if R >= 3 * cnt:
+            for mt in range((cnt + 1) // 2):                         # the kernel's row tiles: two nodes each,
+                for gid in range(8):                                 # rows 0-2 and 4-6 (3 and 7 stay empty)
+                    s, d = 2 * mt + gid // 4, gid % 4
+                    if d == 3 or s >= cnt:
                         continue
-                    d, s = R // cnt, R % cnt
                     na = (perm >> (4 * s)) & 7
                     slot = (slotw >> (4 * na)) & 0xF
                     a = cells[e, na]
