@@ -3,18 +3,19 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--grid 200] [--impl feb200|reference]
 
-N=1 workload (BASELINE.json configs[1]): 3-D hex8 linear elasticity on a uniform n^3 grid (n=200: 8 M
-elements, 24.4 M DoFs, 1.95e9 non-zeros), interior nodes jittered, isotropic material with a Young's modulus per
-quadrature point (--layout EQM, the default; M / EM = one material for the batch / per element).
-One "step" = one assembly pass of the whole mesh through the fe_jax call surface:
-calculate_residual_w_dirichlet + Jacobian CSR values at u_w + Dirichlet elimination of the matrix.
-`value` = elements / s with all inputs resident in HBM (CUDA events around the timed region);
-`e2e` = the same pass with the solution vector coming from pinned host memory and the residual + Jacobian
-diagonal read back to the host inside the timed region (copies on a second stream: u's under the Jacobian kernel,
-which does not read u for linear elasticity, the diagonal's under the residual kernels).  The Newton-CG step (assembly + 100 CG iterations
-+ update + residual) is reported in `newton_cg`.  N>1 (torchrun): every rank assembles its own x-slab
-of an (N*n) x n x n grid (weak scaling, no data-path collective in assembly); `newton_cg` then uses the
-NCCL halo-sum + all-reduce path.
+Workload (BASELINE.json configs[1]): 3-D hex8 linear elasticity on a uniform n^3 grid (n=200: 8 M elements, 24.4 M DoFs,
+1.95e9 non-zeros), interior nodes jittered, isotropic material with a Young's modulus per quadrature point (--layout EQM,
+the default; M / EM = one material for the batch / per element).  One "step" = one assembly pass of the whole mesh
+through the fe_jax call surface: calculate_residual_w_dirichlet + calculate_jacobian_w_dirichlet (CSR values of J_w at u_w
+with the Dirichlet elimination fused).  `value` = elements / s with all inputs resident in HBM (CUDA events around the
+timed region); `e2e` = the same pass with the solution vector coming from pinned host memory and the residual + Jacobian
+diagonal read back to the host inside the timed region.  `newton_cg` = one Newton iteration with 100 CG iterations through
+linear_solve (assembly + CG + update + residual); `newton_cg_hyperelastic` = the same on the hyperelastic problem
+(BASELINE configs[2]).
+N > 1 (torchrun): STRONG scaling -- the same global n^3 grid cut into N x-slabs of n/N element layers, one per GPU; the
+residual's interface halo-sum (NCCL) is inside the timed assembly step, the CG loop runs through the C data plane
+(csrc/dist.cu: halo-sum after every local SpMV, all-reduced dot products).  `parity` compares a converged partitioned
+solve with the single-GPU solve; `weak` is the secondary block with n^3 elements per GPU.
 """
 import argparse
 import json
@@ -51,6 +52,9 @@ def parse():
                     help="hyper = BASELINE configs[2]: hyperelastic (St. Venant-Kirchhoff) residual and tangent, generic two-pass "
                          "assembly; the CPU baseline legs stay on the linear workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hyper", action="store_true", help="skip the hyperelastic (BASELINE configs[2]) Newton-CG block")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the partitioned-vs-single-GPU parity solve")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the secondary weak-scaling block")
     ap.add_argument("--two-pass", action="store_true", help="also time the generic two-pass assembly kernels")
     return ap.parse_args()
 
@@ -203,6 +207,31 @@ def emit(line: dict):
         os.write(_REAL_STDOUT, data)
 
 
+class Problem:
+    """One rank's problem: mesh slab, batch, Dirichlet data, the collection / maps / plan of the fe_jax surface."""
+
+    def __init__(self, fj, torch, dev, nx, n, layout, hyper, x0, x1, x_hi_global, right_val):
+        self.Vx, self.cells, self.mp = make_problem(nx, n, layout, x0=x0, x1=x1)
+        self.E, self.V = self.cells.shape[0], self.Vx.shape[0]
+        self.F = 3 * self.V
+        fe = fj.FiniteElementType(fj.CellType.hexahedron, fj.ElementFamily.P, 1, fj.LagrangeVariant.equispaced,
+                                  fj.QuadratureType.default, 2)
+        self.token = fj.hyperelasticity_residual if hyper else fj.linear_elasticity_residual
+        self.batch = fj.ElementBatch(fe_type=fe, n_dofs_per_basis=3, connectivity_en=self.cells,
+                                     constitutive_model=fj.st_venant_kirchhoff if hyper else fj.elastic_isotropic,
+                                     material_params=self.mp)
+        # Dirichlet: global face x = 0 fixed, global face x = x_hi_global: u_x = right_val
+        xs = self.Vx[:, 0]
+        self.left = np.nonzero(xs < 1e-12)[0]
+        self.right = np.nonzero(xs > x_hi_global - 1e-12)[0]
+        self.bc_v = np.concatenate([np.repeat(self.left, 3), self.right])
+        self.bc_c = np.concatenate([np.tile(np.arange(3), self.left.size), np.zeros(self.right.size, dtype=np.int64)])
+        self.bc_val = np.concatenate([np.zeros(3 * self.left.size), np.full(self.right.size, right_val)])
+        # hyperelastic runs keep the random state in the small-strain range so the tangent stays positive definite
+        self.u_host = torch.from_numpy((1e-5 if hyper else 1e-3) * np.random.default_rng(1).uniform(size=self.F)).pin_memory()
+        self.u = self.u_host.to(dev)
+
+
 def main():
     args = parse()
     _protect_stdout()
@@ -227,53 +256,13 @@ def main():
             dist.barrier()
     import fe_jax as fj
     from fe_jax import _lib
-    from fe_jax.assembly import _assemble_values, _plan, csr_diagonal
-    from fe_jax.krylov import cg_on_pattern
+    from fe_jax import partition as part
+    from fe_jax.assembly import _plan, csr_diagonal
 
     dev = torch.device("cuda", local_rank)
     n = args.n
-    # rank r owns the x-slab [r, r+1] of an (world*n) x n x n grid (weak scaling)
-    Vx, cells, mp = make_problem(n, n, args.layout, x0=float(rank), x1=float(rank + 1))
-    E, V = cells.shape[0], Vx.shape[0]
-    F = 3 * V
-    fe = fj.FiniteElementType(fj.CellType.hexahedron, fj.ElementFamily.P, 1, fj.LagrangeVariant.equispaced,
-                              fj.QuadratureType.default, 2)
-    hyper = args.physics == "hyper"
-    batch = fj.ElementBatch(fe_type=fe, n_dofs_per_basis=3, connectivity_en=cells,
-                            constitutive_model=fj.st_venant_kirchhoff if hyper else fj.elastic_isotropic, material_params=mp)
-    t_setup = time.perf_counter()
-    ebc = fj.batch_to_collection(Vx, [batch])
-    maps = [fj.mesh_to_sparse_assembly_map(V, cells)]
-    plan = _plan(ebc, maps)
-    pat = plan.pattern
-    torch.cuda.synchronize()
-    t_setup = time.perf_counter() - t_setup
-    nnz = pat.nnz
-
-    # Dirichlet: global face x=0 fixed, global face x=world: u_x = 0.01
-    mask = torch.zeros(F, dtype=torch.float64, device=dev)
-    values = torch.zeros(F, dtype=torch.float64, device=dev)
-    xs = torch.from_numpy(Vx[:, 0]).to(dev)
-    left = (xs < 1e-12).nonzero().reshape(-1)
-    right = (xs > world - 1e-12).nonzero().reshape(-1)
-    for c in range(3):
-        mask[3 * left + c] = 1.0
-    mask[3 * right] = 1.0
-    right_val = 0.0005 * world if args.physics == "hyper" else 0.01
-    values[3 * right] = right_val
-    dofs = mask.nonzero().reshape(-1)
-    # hyperelastic runs keep the random state in the small-strain range (h = 1/n) so the tangent stays positive definite
-    u_host = torch.from_numpy((1e-5 if hyper else 1e-3) * np.random.default_rng(1).uniform(size=F)).pin_memory()
-    u = u_host.to(dev)
-    token = fj.hyperelasticity_residual if hyper else fj.linear_elasticity_residual
-    J_vals = torch.empty(nnz, dtype=torch.float64, device=dev)
-    R_host = torch.empty(F, dtype=torch.float64).pin_memory()
-    diag_host = torch.empty(F, dtype=torch.float64).pin_memory()
-
-    def assembly_step():
-        R, _ = fj.calculate_residual_w_dirichlet(token, ebc, maps, u, values, mask)
-        _assemble_values(token, ebc, maps, u, mask, values, out=J_vals, eliminate=True)   # Dirichlet elimination fused
-        return R
+    assert n % world == 0, "the grid size must be divisible by the number of GPUs (x-slabs of n / N element layers)"
+    hyper_main = args.physics == "hyper"
 
     def barrier():
         if world > 1:
@@ -298,10 +287,101 @@ def main():
             ms = float(t.item())
         return ms / steps, _lib.launches - l0
 
+    class Runner:
+        """Assembly / Newton-CG steps of one problem through the fe_jax call surface: the single-GPU functions for N = 1,
+        the element-partitioned driver (fe_jax.partition, NCCL halo-sum + all-reduced CG scalars) for N > 1."""
+
+        def __init__(self, pr: Problem):
+            self.pr = pr
+            t0 = time.perf_counter()
+            if world == 1:
+                self.ebc = fj.batch_to_collection(pr.Vx, [pr.batch])
+                self.maps = [fj.mesh_to_sparse_assembly_map(pr.V, pr.cells)]
+                self.plan = _plan(self.ebc, self.maps)
+                self.pat = self.plan.pattern
+                self.mask = torch.zeros(pr.F, dtype=torch.float64, device=dev)
+                self.values = torch.zeros(pr.F, dtype=torch.float64, device=dev)
+                dofs = torch.from_numpy(3 * pr.bc_v + pr.bc_c).to(dev)
+                self.mask[dofs] = 1.0
+                self.values[dofs] = torch.from_numpy(pr.bc_val).to(dev)
+                self.dofs, self.dvals = dofs, torch.from_numpy(pr.bc_val).to(dev)
+                self.dp = None
+            else:
+                nx = pr.cells.shape[0] // (n * n)
+                ids = np.arange(pr.V).reshape(nx + 1, n + 1, n + 1)
+                lm = part.slab_local_mesh(rank, world, pr.Vx, pr.cells, ids[0].ravel(), ids[nx].ravel())
+                self.dp = part.DistributedProblem(fj, part.TorchDistComm(), [lm], lambda m: [pr.batch],
+                                                  lambda m: (np.stack([pr.bc_v, pr.bc_c], axis=1), pr.bc_val), [dev], pr.token)
+                rp = self.dp.rp[0]
+                self.ebc, self.maps, self.plan, self.pat = rp.ebc, rp.maps, rp.plan, rp.plan.pattern
+                self.mask, self.values, self.dofs, self.dvals = rp.mask_g, rp.values_g, rp.dofs, rp.values
+                self.lm = lm
+            self.J_vals = torch.empty(self.pat.nnz, dtype=torch.float64, device=dev)
+            torch.cuda.synchronize()
+            self.setup_s = time.perf_counter() - t0
+
+        # one assembly pass: R_w(u) (N > 1: with the interface halo-sum) and the CSR values of J_w(u)
+        def assembly_step(self):
+            pr = self.pr
+            if self.dp is None:
+                R, _ = fj.calculate_residual_w_dirichlet(pr.token, self.ebc, self.maps, pr.u, self.values, self.mask)
+                fj.calculate_jacobian_w_dirichlet(pr.token, self.ebc, self.maps, pr.u, self.values, self.mask, None,
+                                                  out=self.J_vals)
+                return R
+            R = self.dp.residual_w_dirichlet([pr.u])[0]
+            self.dp.jacobian_w_dirichlet([pr.u], outs=[self.J_vals])
+            return R
+
+        # one Newton iteration with a fixed number of CG iterations: assembly, solve, update, residual re-evaluation
+        def newton_cg_step(self, cg_iters):
+            pr = self.pr
+            if self.dp is None:
+                opts = fj.SolverOptions(linear_solve_type=fj.LinearSolverType.CG_JAX_SCIPY_W_INFO,
+                                        linear_precond_type=fj.PreconditionerType.NONE, linear_relative_tol=0.0,
+                                        linear_absolute_tol=0.0, linear_max_iter=cg_iters)
+                res = fj.Residual(function=lambda x: fj.calculate_residual_w_dirichlet(
+                    pr.token, self.ebc, self.maps, x, self.values, self.mask)[0], dirichlet_bcs_builtin=True)
+                jac = fj.Jacobian(function=lambda x: fj.calculate_jacobian_w_dirichlet(
+                    pr.token, self.ebc, self.maps, x, self.values, self.mask, None, out=self.J_vals), dirichlet_bcs_builtin=True)
+                info0 = fj.init_solver_info(opts, device=dev)
+                dx, info = fj.linear_solve(res, jac, None, self.dofs, self.dvals, opts, info0, False, pr.u)
+                R2, _ = fj.calculate_residual_w_dirichlet(pr.token, self.ebc, self.maps, pr.u + dx, self.values, self.mask)
+                hist = info.cumulative_residual_norm_history
+                return int(info.cumulative_linear_iterations), hist, R2
+            rp = self.dp.rp[0]
+            Rs = self.dp.residual_w_dirichlet([pr.u])
+            J = self.dp.jacobian_w_dirichlet([pr.u], outs=[self.J_vals])
+            b = (-Rs[0]).contiguous()
+            dx0 = torch.zeros_like(b)
+            dx0[rp.dofs] = rp.values - pr.u[rp.dofs]
+            dxs, k, hist = self.dp.cg(J, [b], [dx0], 0.0, 0.0, cg_iters, jacobi=False, poll_every=cg_iters)
+            dxs[0][rp.dofs] = rp.values - pr.u[rp.dofs]
+            R2 = self.dp.residual_w_dirichlet([pr.u + dxs[0]])
+            return k, hist, R2[0]
+
+        def newton_block(self, cg_iters, steps, ms_assembly, note):
+            ms, _ = timed(lambda: self.newton_cg_step(cg_iters), max(1, steps // 2), 1)
+            k, hist, _ = self.newton_cg_step(cg_iters)
+            out = {"step_ms": ms, "cg_iters": cg_iters, "ms_per_cg_iter": (ms - ms_assembly) / max(cg_iters, 1),
+                   "residual_norm_first": float(hist[0]), "residual_norm_last": float(hist[min(k, cg_iters) - 1]), "note": note}
+            if self.dp is not None:
+                out["interface_dofs_per_rank"] = int(3 * self.lm.n_shared)
+                out["data_plane"] = "C (feb200_cg_iterate_dist: own NCCL communicator)" if self.dp.plane is not None else "torch.distributed"
+            return out
+
+    # ---- main workload: global n^3 grid (N > 1: cut into N x-slabs of n / N element layers, strong scaling)
+    nx = n // world
+    pr = Problem(fj, torch, dev, nx, n, args.layout, hyper_main, rank / world, (rank + 1) / world, 1.0,
+                 0.0005 if hyper_main else 0.01)
+    run = Runner(pr)
+    E, V, F, nnz, pat, plan, ebc, maps = pr.E, pr.V, pr.F, run.pat.nnz, run.pat, run.plan, run.ebc, run.maps
+    token, u, mask, values, J_vals = pr.token, pr.u, run.mask, run.values, run.J_vals
+    total_E = n * n * n
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_step, launches = timed(assembly_step, args.steps, args.warmup)
+    ms_step, launches = timed(run.assembly_step, args.steps, args.warmup)
 
     # ---- per-kernel durations (same inputs, each kernel timed on its own over `steps` launches)
     res = fj.physics.resolve_residual(token)
@@ -310,8 +390,7 @@ def main():
     Rtmp = torch.empty(F, dtype=torch.float64, device=dev)
     row = maps[0].indptr.reshape(-1).view(torch.int64)
     col = maps[0].indices.reshape(-1).view(torch.int64)
-    fused = None if hyper else plan.fused_plan(ebc, 0)          # the fused kernels are for the linear isotropic tangent
-    from fe_jax.assembly import _vertex_flags
+    from fe_jax.assembly import _vertex_flags, _block_flags, _use_tensor_core_kernel, _use_sweep_kernel, _material_hints
     vflags = _vertex_flags(ebc, mask)
     kernels = {
         "element_residual": lambda: _lib.call("feb200_element_residual", bstruct, _lib.ptr(ebc._vertices), _lib.ptr(u),
@@ -319,11 +398,10 @@ def main():
         "scatter_sum": lambda: _lib.call("feb200_scatter_sum", _lib.ptr(row), _lib.ptr(col), V, 3, _lib.ptr(R_e),
                                          _lib.ptr(Rtmp), 0, _lib.ptr(mask), _lib.ptr(values), _lib.ptr(u)),
     }
-    from fe_jax.assembly import _use_tensor_core_kernel, _use_sweep_kernel, _material_hints
-    sweep = plan.sweep_plan(ebc, 0) if (not hyper and _use_sweep_kernel(ebc, 0, bstruct)) else None
-    use_mma = sweep is None and fused is not None and _use_tensor_core_kernel(ebc, 0, bstruct, fused)
+    sweep = plan.sweep_plan(ebc, 0) if (not hyper_main and _use_sweep_kernel(ebc, 0, bstruct)) else None
+    fused = None if (hyper_main or sweep is not None) else plan.fused_plan(ebc, 0)
+    use_mma = fused is not None and _use_tensor_core_kernel(ebc, 0, bstruct, fused)
     if sweep is not None:
-        from fe_jax.assembly import _block_flags
         bflags = _block_flags(ebc, pat, mask)
         kernels["assemble_fused_hex8"] = lambda: _lib.call(
             "feb200_assemble_fused_hex8_sweep", bstruct, sweep.struct, _lib.ptr(ebc._vertices), _lib.ptr(plan.slot_rank[0]),
@@ -336,7 +414,7 @@ def main():
         kernels["assemble_fused_hex8"] = lambda: _lib.call(
             "feb200_assemble_fused_hex8", bstruct, fused.struct, _lib.ptr(ebc._vertices), _lib.ptr(row),
             _lib.ptr(plan.slot_rank[0]), _lib.ptr(pat.nindptr), _lib.ptr(pat.nindices), _lib.ptr(vflags), _lib.ptr(J_vals))
-    if fused is None or args.two_pass:
+    if "assemble_fused_hex8" not in kernels or args.two_pass:
         K_e = ebc._buffer("K_e", E * 8 * 8 * 9)
         kernels["element_tangent"] = lambda: _lib.call("feb200_element_tangent", bstruct, _lib.ptr(ebc._vertices), _lib.ptr(u),
                                                        _lib.ptr(mask), _lib.ptr(values), _lib.ptr(K_e))
@@ -344,96 +422,64 @@ def main():
                                                     _lib.ptr(plan.slot_rank[0]), _lib.ptr(pat.nindptr), pat.max_deg,
                                                     _lib.ptr(J_vals), 0, _lib.ptr(pat.nindices), _lib.ptr(mask))
     kernel_ms = {k: timed(f, args.steps, 1)[0] for k, f in kernels.items()}
-    assemble_step_again = assembly_step()        # leave J_vals / R consistent for the solve below
+    run.assembly_step()                          # leave J_vals / R consistent for the solve below
     xv = torch.rand(F, dtype=torch.float64, device=dev)
     yv = torch.empty_like(xv)
     spmv = lambda: _lib.call("feb200_spmv", pat.V, pat.U, _lib.ptr(pat.nindptr), _lib.ptr(pat.nindices), _lib.ptr(J_vals),
                              _lib.ptr(xv), _lib.ptr(yv), None, None, 0)
     kernel_ms["spmv"] = timed(spmv, max(args.steps, 10), 3)[0]
 
-    # ---- Newton-CG step: assembly + fixed number of CG iterations + update + residual re-evaluation
-    def newton_cg_step():
-        R = assembly_step()
-        b = -R
-        dx0 = torch.zeros_like(b)
-        dx0[dofs] = values[dofs] - u[dofs]
-        dx, k, hist = cg_on_pattern(pat, J_vals, b, dx0, 0.0, 0.0, args.cg_iters, None, poll_every=args.cg_iters)
-        dx[dofs] = values[dofs] - u[dofs]
-        un = u + dx
-        R2, _ = fj.calculate_residual_w_dirichlet(token, ebc, maps, un, values, mask)
-        return k, hist, R2
-
-    ncg_ms = None
-    if world == 1:
-        ncg_ms, _ = timed(newton_cg_step, max(1, args.steps // 2), 1)
-        k, hist, R2 = newton_cg_step()
-        cg_only_ms = (ncg_ms - ms_step) / max(args.cg_iters, 1)
-        newton = {"step_ms": ncg_ms, "cg_iters": args.cg_iters, "ms_per_cg_iter": cg_only_ms,
-                  "residual_norm_first": float(hist[0]), "residual_norm_last": float(hist[min(k, args.cg_iters) - 1]),
-                  "note": "fixed CG iteration count (tol=0): assembly + CG + update + residual re-evaluation"}
-    else:
-        # element-partitioned Newton-CG step: local assembly, NCCL halo-sum of interface DoFs after every local
-        # SpMV / scatter, all-reduced CG scalars (fe_jax/partition.py)
-        from fe_jax import partition as part
-        ids = np.arange(V).reshape(n + 1, n + 1, n + 1)
-        lm = part.slab_local_mesh(rank, world, Vx, cells, ids[0].ravel(), ids[n].ravel())
-        bc_v = np.concatenate([np.repeat(left.cpu().numpy(), 3), right.cpu().numpy()])
-        bc_c = np.concatenate([np.tile(np.arange(3), left.numel()), np.zeros(right.numel(), dtype=np.int64)])
-        bc_val = np.concatenate([np.zeros(3 * left.numel()), np.full(right.numel(), right_val)])
-        dp = part.DistributedProblem(fj, part.TorchDistComm(), [lm], lambda m: [batch],
-                                     lambda m: (np.stack([bc_v, bc_c], axis=1), bc_val), [dev], token)
-        rp = dp.rp[0]
-
-        def dist_newton_cg_step():
-            Rs = dp.residual_w_dirichlet([u])
-            J = dp.jacobian_w_dirichlet([u])
-            b = (-Rs[0]).contiguous()
-            dx0 = torch.zeros_like(b)
-            dx0[rp.dofs] = rp.values - u[rp.dofs]
-            dxs, k, hist = dp.cg(J, [b], [dx0], 0.0, 0.0, args.cg_iters, jacobi=False, poll_every=args.cg_iters)
-            dxs[0][rp.dofs] = rp.values - u[rp.dofs]
-            R2 = dp.residual_w_dirichlet([u + dxs[0]])
-            return k, hist, R2
-
-        ncg_ms, _ = timed(dist_newton_cg_step, max(1, args.steps // 2), 1)
-        k, hist, R2 = dist_newton_cg_step()
-        newton = {"step_ms": ncg_ms, "cg_iters": args.cg_iters, "ms_per_cg_iter": (ncg_ms - ms_step) / max(args.cg_iters, 1),
-                  "residual_norm_first": float(hist[0]), "residual_norm_last": float(hist[min(k, args.cg_iters) - 1]),
-                  "interface_dofs_per_rank": int(3 * lm.n_shared),
-                  "note": "element-partitioned: NCCL halo-sum after each local SpMV/scatter + all-reduced CG scalars"}
+    # ---- Newton-CG step of the main workload (fixed CG iteration count: tol = 0)
+    newton = run.newton_block(args.cg_iters, args.steps, ms_step,
+                              "fixed CG iteration count (tol=0): assembly + CG + update + residual re-evaluation, through "
+                              + ("linear_solve" if world == 1 else "the element-partitioned driver (halo-sum after each local SpMV / "
+                                 "scatter, all-reduced CG scalars)"))
 
     # ---- end to end through the public API with host buffers
     copy_stream = torch.cuda.Stream(device=dev)
-    r_ready = torch.cuda.Event()
+    r_ready, u_ready, j_ready = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+    R_host = torch.empty(F, dtype=torch.float64).pin_memory()
+    diag_host = torch.empty(F, dtype=torch.float64).pin_memory()
+    u_host = pr.u_host
 
-    u_ready, j_ready = torch.cuda.Event(), torch.cuda.Event()
+    def jacobian_only():
+        if run.dp is None:
+            fj.calculate_jacobian_w_dirichlet(token, ebc, maps, u, values, mask, None, out=J_vals)
+        else:
+            run.dp.jacobian_w_dirichlet([u], outs=[J_vals])
+
+    def residual_only():
+        if run.dp is None:
+            return fj.calculate_residual_w_dirichlet(token, ebc, maps, u, values, mask)[0]
+        return run.dp.residual_w_dirichlet([u])[0]
 
     def e2e_step():
         # Both copies finish inside the timed region.  Linear elasticity: the tangent does not depend on u, so the
         # Jacobian kernel starts at once and the host -> device copy of u runs under it on the copy stream; the
         # diagonal's device -> host copy then runs under the residual kernels and only the residual's copy is exposed.
         # Hyperelastic: u first, residual, its copy under the tangent + assembly kernels, then the diagonal's copy.
-        if not hyper:
+        # The CSR values themselves stay device-resident by design (they feed the SpMV of the solve).
+        if not hyper_main:
             with torch.cuda.stream(copy_stream):
                 u.copy_(u_host, non_blocking=True)
                 u_ready.record()
-            _assemble_values(token, ebc, maps, u, mask, values, out=J_vals, eliminate=True)
+            jacobian_only()
             d = csr_diagonal(pat, J_vals)
             j_ready.record()
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(j_ready)
                 diag_host.copy_(d, non_blocking=True)
             torch.cuda.current_stream().wait_event(u_ready)
-            R, _ = fj.calculate_residual_w_dirichlet(token, ebc, maps, u, values, mask)
+            R = residual_only()
             R_host.copy_(R, non_blocking=True)
         else:
             u.copy_(u_host, non_blocking=True)
-            R, _ = fj.calculate_residual_w_dirichlet(token, ebc, maps, u, values, mask)
+            R = residual_only()
             r_ready.record()
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(r_ready)
                 R_host.copy_(R, non_blocking=True)
-            _assemble_values(token, ebc, maps, u, mask, values, out=J_vals, eliminate=True)
+            jacobian_only()
             d = csr_diagonal(pat, J_vals)
             diag_host.copy_(d, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -441,11 +487,43 @@ def main():
     e2e_ms, _ = timed(e2e_step, max(1, args.steps), 1)
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- BASELINE configs[2]: the same mesh with the hyperelastic (St. Venant-Kirchhoff) residual and tangent, Newton-CG step
+    extra = {}
+    if not hyper_main and not args.no_hyper:
+        del kernels
+        run.J_vals = J_vals = None
+        ebc._scratch.clear()
+        torch.cuda.empty_cache()
+        prh = Problem(fj, torch, dev, nx, n, args.layout, True, rank / world, (rank + 1) / world, 1.0, 0.0005)
+        runh = Runner(prh)
+        ms_h, _ = timed(runh.assembly_step, max(2, args.steps // 2), 2)
+        nb = runh.newton_block(args.cg_iters, args.steps, ms_h,
+                               "BASELINE configs[2]: hyperelastic (St. Venant-Kirchhoff) Newton-CG step on the same global mesh, "
+                               "generic two-pass assembly (state-dependent tangent), fixed CG iteration count")
+        nb["assembly_ms"] = ms_h
+        nb["assembly_elements_per_s"] = total_E / (ms_h * 1e-3)
+        extra["newton_cg_hyperelastic"] = nb
+        del runh, prh
+        torch.cuda.empty_cache()
+
+    # ---- N > 1: parity of the partitioned solve against one GPU (32^3 global mesh, converged Jacobi-CG solves)
+    if world > 1 and not args.no_parity:
+        extra["parity"] = partition_parity(fj, part, torch, dist, dev, rank, world, 32)
+    # ---- N > 1: secondary weak-scaling block (n^3 elements PER GPU, the round-1 headline)
+    if world > 1 and not args.no_weak:
+        torch.cuda.empty_cache()
+        prw = Problem(fj, torch, dev, n, n, args.layout, False, float(rank), float(rank + 1), float(world), 0.01)
+        runw = Runner(prw)
+        ms_w, _ = timed(runw.assembly_step, max(2, args.steps // 2), 2)
+        nbw = runw.newton_block(args.cg_iters, args.steps, ms_w, f"weak scaling: {n}^3 elements per GPU, interface halo-sum in the assembly step")
+        extra["weak"] = {"elements_per_gpu": prw.E, "assembly_ms": ms_w, "assembly_elements_per_s": prw.E * world / (ms_w * 1e-3),
+                         "newton_cg": nbw}
+        del runw, prw
+
     if rank == 0:
         hbm, hbm_src = peaks()
-        total_E = E * world
         value = total_E / (ms_step * 1e-3)
-        # algorithmic bytes (the slot map is 2 bytes per node pair here):
+        # algorithmic bytes per rank (the slot map is 2 bytes per node pair here):
         #   Jacobian assembly kernel  B_J = 8 nnz + 2 N^2 E + 4 N E + 8 D V + 8 n_mp (material parameters)
         #   whole assembly pass       B_A = B_J + 8 F (u) + 8 F (R) + 16 F (mask, values) + 8 n_mp
         n_mp = {"M": 2, "EM": 2 * E, "EQM": 16 * E}[args.layout]
@@ -462,21 +540,25 @@ def main():
         achieved = bytes_J / (dom_ms * 1e-3) / 1e9
         traffic = None
         try:        # dram bytes of the dominant kernel from the committed ncu --set full capture of this configuration
-            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-                traffic = json.load(f).get(f"fused{'_mma' if use_mma else ''}_n{n}_{args.layout}") if "assemble_fused_hex8" in kernel_ms else None
+            with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+                key = ("sweep" if sweep is not None else "fused_mma" if use_mma else "fused") + f"_n{n}_{args.layout}"
+                traffic = json.load(f).get(key) if ("assemble_fused_hex8" in kernel_ms and world == 1) else None
         except Exception:
             pass
         spmv_bytes = 8 * nnz + 4 * (nnz // 9) + 8 * (V + 1) + 16 * F
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"3D hex8 linear elasticity, uniform grid {n}^3 elements per GPU (BASELINE configs[1]), "
-                                   f"residual + Jacobian CSR assembly with fused Dirichlet elimination; material layout ({args.layout})"
+            "config": {"workload": f"3D hex8 linear elasticity, uniform grid {n}^3 elements (BASELINE configs[1])"
+                                   + (f" cut into {world} x-slabs of {nx} element layers, one per GPU; interface halo-sum of the "
+                                      f"residual (NCCL) inside the timed step" if world > 1 else "")
+                                   + f", residual + Jacobian CSR assembly with fused Dirichlet elimination through "
+                                     f"calculate_residual_w_dirichlet + calculate_jacobian_w_dirichlet; material layout ({args.layout})"
                                    + ("; HYPERELASTIC (St. Venant-Kirchhoff) residual and tangent, generic two-pass assembly "
-                                      "(BASELINE configs[2])" if hyper else ""),
-                       "elements_per_gpu": E, "dofs_per_gpu": F, "nnz_per_gpu": nnz, "l2_policy": "inputs larger than L2",
-                       "setup_s": t_setup},
+                                      "(BASELINE configs[2])" if hyper_main else ""),
+                       "elements_total": total_E, "elements_per_gpu": E, "dofs_per_gpu": F, "nnz_per_gpu": nnz,
+                       "l2_policy": "inputs larger than L2", "setup_s": run.setup_s},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s",
                          "frac": achieved / hbm, "traffic": traffic, "peak_source": hbm_src, "algorithmic_bytes": bytes_J,
                          "kernel_ms": kernel_ms,
@@ -486,18 +568,111 @@ def main():
                                   "frac": spmv_bytes / (kernel_ms["spmv"] * 1e-3) / 1e9 / hbm, "algorithmic_bytes": spmv_bytes}},
             "newton_cg": newton,
             "e2e": {"value": total_E / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * F,
-                    "d2h_bytes_per_step": 16 * F, "ms_per_step": e2e_ms},
+                    "d2h_bytes_per_step": 16 * F, "ms_per_step": e2e_ms,
+                    "note": "per rank: u from pinned host memory, R and diag(J) back; the CSR values stay device-resident by design"},
             "gpu_launches": launches,
             "clocks": clocks,
         }
+        line.update(extra)
         if not args.no_cpu_baseline and world == 1:
-            eps, sec, Ec, cores = cpu_reference_parallel(args.cpu_n, layout=args.layout)
-            line["cpu_baseline"] = {"value": eps, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"oracle reference-style assembly on a {args.cpu_n}^3 hex8 grid ({Ec} elements, "
-                                              f"{sec:.1f} s) on {cores} host cores concurrently (aggregate)"}
+            line["cpu_baseline"] = cpu_baseline_block(args, fj, _lib, torch, dev)
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def partition_parity(fj, part, torch, dist, dev, rank, world, n):
+    """A converged linear-elasticity solve (Jacobi-CG to a relative residual of 1e-12) of the jittered n^3 grid cut into
+    `world` element ranges and solved over NCCL, against the same solve on one GPU (every rank runs the single-GPU solve of
+    this small problem itself): largest relative difference of the solutions over all ranks and the CG iteration counts."""
+    Vx, cells = fj.uniform_hex_grid(n, n, n)
+    rng = np.random.default_rng(0)
+    interior = np.all((Vx > 1e-12) & (Vx < 1 - 1e-12), axis=1)
+    Vx = Vx + 0.2 / n * rng.uniform(-1.0, 1.0, size=Vx.shape) * interior[:, None]
+    mp = np.array([70e9, 0.25])
+    fe = fj.FiniteElementType(fj.CellType.hexahedron, fj.ElementFamily.P, 1, fj.LagrangeVariant.equispaced,
+                              fj.QuadratureType.default, 2)
+    left = np.nonzero(Vx[:, 0] < 1e-12)[0]
+    right = np.nonzero(Vx[:, 0] > 1 - 1e-12)[0]
+    bcs = np.concatenate([np.stack([np.repeat(left, 3), np.tile(np.arange(3), left.size)], axis=1),
+                          np.stack([right, np.zeros(right.size, dtype=np.int64)], axis=1)])
+    vals = np.concatenate([np.zeros(3 * left.size), np.full(right.size, 0.01)])
+    opts = fj.SolverOptions(linear_precond_type=fj.PreconditionerType.JACOBI, linear_relative_tol=1e-12,
+                            linear_absolute_tol=0.0, linear_max_iter=2000, nonlinear_max_iter=1)
+    token = fj.linear_elasticity_residual
+    make = lambda c: fj.ElementBatch(fe_type=fe, n_dofs_per_basis=3, connectivity_en=c, constitutive_model=fj.elastic_isotropic,
+                                     material_params=mp)
+    u_ref, _, _ = fj.solve_bvp(Vx, [make(cells)], token, None, bcs, vals, solver_options=opts)
+    it_ref = int(fj.solve_bvp.last_info.cumulative_linear_iterations)
+    lm = part.partition_mesh(Vx, cells, world)[rank]
+    g = lm.global_vertex_ids
+
+    def dirichlet_local(m):
+        keep = np.isin(bcs[:, 0], g)
+        loc = np.stack([np.searchsorted(g, bcs[keep, 0]), bcs[keep, 1]], axis=1)
+        return loc, vals[keep]
+
+    dp = part.DistributedProblem(fj, part.TorchDistComm(), [lm], lambda m: [make(m.cells)], dirichlet_local, [dev], token)
+    rp = dp.rp[0]
+    us, info = dp.newton([torch.zeros(rp.F, dtype=torch.float64, device=dev)], opts)
+    gd = torch.from_numpy(g).to(dev)
+    ref_loc = u_ref.view(-1, 3)[gd].reshape(-1)
+    err = ((us[0] - ref_loc).abs().max() / u_ref.abs().max()).reshape(1)
+    dist.all_reduce(err, op=dist.ReduceOp.MAX)
+    it_par = int(info["linear_iterations"][0]) if info["linear_iterations"] else -1
+    return {"mesh": f"hex8 {n}^3 jittered, linear elasticity, Jacobi-CG rtol 1e-12, {world} element ranges over NCCL vs one GPU",
+            "max_rel": float(err.item()), "iterations_partitioned": it_par, "iterations_single_gpu": it_ref,
+            "iterations_equal": it_par == it_ref,
+            "data_plane": "C (feb200_halo_sum / feb200_cg_iterate_dist)" if dp.plane is not None else "torch.distributed"}
+
+
+def cpu_baseline_block(args, fj, _lib, torch, dev):
+    """CPU legs beside the GPU numbers, bounded to tens of seconds: the oracle's reference-style
+    assembly at 32^3 on every host core at once, and a SciPy-CSR CG iteration (SpMV + the vector updates of
+    solve_cg.py:20-63) on the 64^3 matrix -- assembled on the GPU and copied to the host, because the reference-style CPU
+    assembly of that size alone would take minutes."""
+    n_a = max(args.cpu_n, 32) if args.cpu_n >= 20 else args.cpu_n
+    eps, sec, Ec, cores = cpu_reference_parallel(n_a, layout=args.layout)
+    out = {"value": eps, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": f"oracle reference-style assembly (per-element K_e + COO lexsort + duplicate sum) on a {n_a}^3 hex8 grid "
+                     f"({Ec} elements, {sec:.1f} s) on {cores} host cores concurrently (aggregate)"}
+    try:
+        import scipy.sparse as sp
+        m = 64 if args.cpu_n >= 20 else 8
+        Vx, cells, mp = make_problem(m, m, "M")
+        fe = fj.FiniteElementType(fj.CellType.hexahedron, fj.ElementFamily.P, 1, fj.LagrangeVariant.equispaced,
+                                  fj.QuadratureType.default, 2)
+        batch = fj.ElementBatch(fe_type=fe, n_dofs_per_basis=3, connectivity_en=cells, constitutive_model=fj.elastic_isotropic,
+                                material_params=mp)
+        ebc = fj.batch_to_collection(Vx, [batch])
+        maps = [fj.mesh_to_sparse_assembly_map(Vx.shape[0], cells)]
+        F = 3 * Vx.shape[0]
+        mask = torch.zeros(F, dtype=torch.float64, device=dev)
+        mask[:3 * (m + 1) ** 2] = 1.0
+        J = fj.calculate_jacobian_w_dirichlet(fj.linear_elasticity_residual, ebc, maps, torch.zeros(F, dtype=torch.float64, device=dev),
+                                              torch.zeros_like(mask), mask)
+        csr = fj.coo_to_csr(J)
+        A = sp.csr_matrix((csr.data.cpu().numpy(), csr.indices.cpu().numpy(), csr.indptr.cpu().numpy()), shape=(F, F))
+        rng = np.random.default_rng(0)
+        b = rng.normal(size=F)
+        x, r = np.zeros(F), b.copy()
+        p, gamma = r.copy(), float(r @ r)
+        its, t0 = 20, time.perf_counter()
+        for _ in range(its):
+            Ap = A @ p
+            alpha = gamma / float(p @ Ap)
+            x += alpha * p
+            r -= alpha * Ap
+            g2 = float(r @ r)
+            p = r + (g2 / gamma) * p
+            gamma = g2
+        dt = (time.perf_counter() - t0) / its
+        out["cg"] = {"ms_per_iteration": dt * 1e3, "grid": f"{m}^3 hex8 ({F} DoFs, {A.nnz} non-zeros)", "cores": 1,
+                     "kind": "scipy.sparse CSR SpMV + NumPy vector updates (solve_cg.py:20-63 recurrence), matrix assembled "
+                             "on the GPU and copied to the host"}
+    except Exception as exc:                       # the CG leg is additional context; the assembly leg is the baseline
+        out["cg"] = {"error": repr(exc)}
+    return out
 
 
 if __name__ == "__main__":

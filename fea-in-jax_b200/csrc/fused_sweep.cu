@@ -145,14 +145,15 @@ __device__ __forceinline__ void sweep_rows(const double* __restrict__ Ge, const 
     double C[NMT][3][2];
 #pragma unroll
     for (int mt = 0; mt < NMT; ++mt) {
-        const int R = 8 * mt + gid;
 #if FEB_SW_ROWS6
         const int s = 2 * mt + (gid >> 2), d = gid & 3;
         valid[mt] = d < 3 && s < cnt;
 #elif FEB_SW_DMAJOR
+        const int R = 8 * mt + gid;
         const int d = (R >= cnt ? 1 : 0) + (R >= 2 * cnt ? 1 : 0), s = R - d * cnt;
         valid[mt] = R < 3 * cnt;
 #else
+        const int R = 8 * mt + gid;
         const int s = R / 3, d = R - 3 * s;
         valid[mt] = s < cnt;
 #endif

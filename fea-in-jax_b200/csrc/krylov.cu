@@ -68,7 +68,10 @@ __global__ void __launch_bounds__(256) k_spmv(int64_t V, const int64_t* __restri
                                               const int32_t* __restrict__ nindices, const double* __restrict__ values,
                                               const double* __restrict__ x, double* __restrict__ y, double* dot_out,
                                               ReduceWs ws, const int32_t* counters, double* scalars) {
-    if (counters && counters[C_DONE]) return;
+    if (counters && counters[C_DONE]) {       // finished: leave a zero partial (an all-reduce of a stale one would grow it)
+        if (scalars && blockIdx.x == 0 && threadIdx.x == 0) scalars[S_PAP] = 0.0;
+        return;
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     double d[1] = {0.0};
     for (int64_t a = (int64_t)blockIdx.x * wpb + warp; a < V; a += (int64_t)gridDim.x * wpb)
@@ -163,7 +166,10 @@ __global__ void __launch_bounds__(SPB_WARPS * 32, FEB_SPMV_CTAS)
 k_spmv3_bulk(int64_t V, const int64_t* __restrict__ nindptr, const int32_t* __restrict__ nindices,
              const double* __restrict__ values, const double* __restrict__ x, double* __restrict__ y, double* dot_out,
              ReduceWs ws, const int32_t* counters, double* scalars) {
-    if (counters && counters[C_DONE]) return;
+    if (counters && counters[C_DONE]) {
+        if (scalars && blockIdx.x == 0 && threadIdx.x == 0) scalars[S_PAP] = 0.0;
+        return;
+    }
     extern __shared__ __align__(16) unsigned char spb_smem[];
     __shared__ __align__(8) uint64_t bars[SPB_WARPS * SPB_NB];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -342,7 +348,10 @@ __global__ void k_spmv_csr(int64_t n_rows, const int64_t* __restrict__ indptr, c
 __global__ void __launch_bounds__(256) k_dot(int64_t n, const double* __restrict__ a, const double* __restrict__ b,
                                              const double* __restrict__ w, double* out, ReduceWs ws,
                                              const int32_t* counters) {
-    if (counters && counters[C_DONE]) return;
+    if (counters && counters[C_DONE]) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = 0.0;
+        return;
+    }
     double d[1] = {0.0};
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         d[0] += w ? w[i] * (a[i] * b[i]) : a[i] * b[i];
@@ -401,7 +410,10 @@ __global__ void __launch_bounds__(256) k_cg_update_xr(int64_t n, const double* _
                                                       const double* __restrict__ inv_diag, const double* __restrict__ w,
                                                       double* __restrict__ x, double* __restrict__ r, double* scalars,
                                                       const int32_t* counters, ReduceWs ws, int vec2) {
-    if (counters[C_DONE]) return;
+    if (counters[C_DONE]) {
+        if (w && blockIdx.x == 0 && threadIdx.x == 0) { scalars[S_GAMMA_NEW] = 0.0; scalars[S_RR] = 0.0; }   // partial sums of a partitioned run
+        return;
+    }
     const double alpha = scalars[S_GAMMA] / scalars[S_PAP];
     double d[2] = {0.0, 0.0};
     auto one = [&](int64_t i) {

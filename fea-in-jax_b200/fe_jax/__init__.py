@@ -18,8 +18,8 @@ from .physics import (elastic_isotropic, elastic_orthotropic, st_venant_kirchhof
                       linear_elasticity_residual, hyperelasticity_residual)
 from .assembly import (ElementBatch, ElementBatchCollection, MaterialPropertyArrayType, QuadratureArrayType,
                        batch_to_collection, _calculate_jacobian_unique_nnz, calculate_jacobian_wo_dirichlet,
-                       calculate_jacobian_diag_wo_dirichlet, calculate_residual_wo_dirichlet,
-                       calculate_residual_w_dirichlet)
+                       calculate_jacobian_w_dirichlet, calculate_jacobian_diag_wo_dirichlet,
+                       calculate_residual_wo_dirichlet, calculate_residual_w_dirichlet)
 from .sparse import (coo_arrays_sum_duplicates, coo_arrays_sum_duplicates_jit, coo_sum_duplicates, coo_to_csr,
                      apply_dirichlet_bcs_lhs, apply_dirichlet_bcs_rhs)
 from .krylov import cg, JacobiPreconditioner

@@ -49,6 +49,15 @@ class SweepPlan(Structure):
                 ("seg_visit_ptr", c_void_p), ("seg_chunk_ptr", c_void_p), ("visits", c_void_p), ("chunk_rec", c_void_p)]
 
 
+MAX_NEIGHBOURS = 8
+
+
+class Halo(Structure):
+    _fields_ = [("n_neighbours", c_int32), ("U", c_int32), ("peer", c_int32 * MAX_NEIGHBOURS), ("reserved", c_int32 * 2),
+                ("count", c_int64 * MAX_NEIGHBOURS), ("idx", c_void_p * MAX_NEIGHBOURS), ("send", c_void_p * MAX_NEIGHBOURS),
+                ("recv", c_void_p * MAX_NEIGHBOURS)]
+
+
 class CGState(Structure):
     _fields_ = [("V", c_int64), ("U", c_int32), ("maxiter", c_int32),
                 ("nindptr", c_void_p), ("nindices", c_void_p), ("values", c_void_p), ("inv_diag", c_void_p),
@@ -102,6 +111,16 @@ SIGNATURES = {
     "feb200_cg_init": (c_int32, [_P, POINTER(CGState), _F64, _F64]),
     "feb200_cg_iterate": (c_int32, [_P, POINTER(CGState), _I32]),
     "feb200_cg_stage": (c_int32, [_P, POINTER(CGState), _I32, _F64, _F64]),
+    "feb200_nccl_available": (c_int32, []),
+    "feb200_nccl_unique_id": (c_int32, [_P]),
+    "feb200_nccl_comm_init": (c_int32, [_I32, _I32, _P, POINTER(c_void_p)]),
+    "feb200_nccl_comm_destroy": (c_int32, [_P]),
+    "feb200_halo_pack": (c_int32, [_P, POINTER(Halo), _P]),
+    "feb200_halo_unpack_add": (c_int32, [_P, POINTER(Halo), _P]),
+    "feb200_halo_sum": (c_int32, [_P, _P, POINTER(Halo), _P]),
+    "feb200_dot_allreduce": (c_int32, [_P, _P, _P, _I32]),
+    "feb200_cg_init_dist": (c_int32, [_P, _P, POINTER(CGState), POINTER(Halo), _F64, _F64]),
+    "feb200_cg_iterate_dist": (c_int32, [_P, _P, POINTER(CGState), POINTER(Halo), _I32]),
     "feb200_bcg_init": (c_int32, [_P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _F64, _F64, _I32]),
     "feb200_bcg_step": (c_int32, [_P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _I32]),
     "feb200_axpby": (c_int32, [_P, _I64, _F64, _P, _F64, _P, _P]),

@@ -512,6 +512,23 @@ def calculate_jacobian_wo_dirichlet(element_residual_func, ebc: ElementBatchColl
     return COO((vals,), shape=(F, F), rows_sorted=True, pattern=pat)
 
 
+def calculate_jacobian_w_dirichlet(element_residual_func, ebc: ElementBatchCollection, assembly_map_b, u_f,
+                                   dirichlet_values_g, dirichlet_mask_g, precomputed_jacobian_nnz: int = None, out=None):
+    """J_w = (I-M) J(u_w) (I-M) + M with u_w = (1-m) u + m g, as a sorted-unique COO on the node pattern: the Jacobian
+    builder that goes with calculate_residual_w_dirichlet.  It is the operator the reference's CG applies as a JVP of
+    R_w (sparse_linear_solve.py:251-258) and equals apply_dirichlet_bcs_lhs(calculate_jacobian_wo_dirichlet(u_w))
+    (sparse_matrix.py:157-184); here the elimination is fused into the assembly store.  `out` (nnz doubles) is reused
+    for the values when given."""
+    u = _as_u(ebc, u_f)
+    g = as_device(dirichlet_values_g, torch.float64)
+    m = as_device(dirichlet_mask_g, torch.float64)
+    vals, pat = _assemble_values(element_residual_func, ebc, assembly_map_b, u, m, g, out=out, eliminate=True)
+    if precomputed_jacobian_nnz is not None and int(precomputed_jacobian_nnz) != pat.nnz:
+        raise _lib.Feb200Error(f"precomputed_jacobian_nnz={precomputed_jacobian_nnz} but the pattern has {pat.nnz} entries")
+    F = u.shape[0]
+    return COO((vals,), shape=(F, F), rows_sorted=True, pattern=pat)
+
+
 def calculate_jacobian_diag_wo_dirichlet(element_residual_func, ebc: ElementBatchCollection, assembly_map_b, u_f):
     """diag(J) (F,) (fea.py:759-797) -- read off the deterministically assembled CSR."""
     u = _as_u(ebc, u_f)

@@ -7,8 +7,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from .assembly import (ElementBatchCollection, _assemble_values, _plan, batch_to_collection,
-                       calculate_jacobian_diag_wo_dirichlet, calculate_residual_w_dirichlet)
+from .assembly import (ElementBatchCollection, _plan, batch_to_collection, calculate_jacobian_diag_wo_dirichlet,
+                       calculate_jacobian_w_dirichlet, calculate_residual_w_dirichlet)
 from .containers import COO
 from .mesh import as_device, mesh_to_sparse_assembly_map
 from .solver import Jacobian, JacobianDiagonl, Residual, SolverOptions, init_solver_info, linear_solve
@@ -45,11 +45,9 @@ def solve_nonlinear_step(element_residual_func, ebc: ElementBatchCollection, ass
         # J_w = (I-M) J(u_w) (I-M) + M, assembled at u_w = (1-m) u + m g with the elimination fused into the
         # assembly store: this is the operator the reference's CG branch applies (JVP of R_w at x_0,
         # sparse_linear_solve.py:251-258); identical to apply_dirichlet_bcs_lhs(J(u_f)) for linear problems
-        u = as_device(u_f, torch.float64)
-        vals, pat = _assemble_values(element_residual_func, ebc, assembly_map_b, u, mask_g, values_g, eliminate=True)
-        if jacobian_nnz is not None and int(jacobian_nnz) != pat.nnz:
-            raise _lib.Feb200Error(f"jacobian_nnz={jacobian_nnz} but the pattern has {pat.nnz} entries")
-        return COO((vals,), shape=(u.shape[0], u.shape[0]), rows_sorted=True, pattern=pat)
+        return calculate_jacobian_w_dirichlet(element_residual_func=element_residual_func, ebc=ebc,
+                                              assembly_map_b=assembly_map_b, u_f=u_f, dirichlet_values_g=values_g,
+                                              dirichlet_mask_g=mask_g, precomputed_jacobian_nnz=jacobian_nnz)
 
     def jacobian_diag_func_wo_dirichlet(u_f):
         return calculate_jacobian_diag_wo_dirichlet(element_residual_func=element_residual_func, ebc=ebc,

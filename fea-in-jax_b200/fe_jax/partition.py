@@ -104,7 +104,7 @@ class InProcessComm:
 
     def exchange(self, send):
         """send[r][p] = tensor rank r sends to p  ->  recv[r][p] = tensor r receives from p"""
-        return [{p: send[p][r] for p in send[r]} for r in range(self.world)]
+        return [{p: send[p][r].to(send[r][p].device) for p in send[r]} for r in range(self.world)]
 
     def all_reduce_sum(self, tensors):
         total = tensors[0].clone()
@@ -139,6 +139,61 @@ class TorchDistComm:
     def all_reduce_sum(self, tensors):
         (t,) = tensors
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+
+
+class NcclDataPlane:
+    """The C data plane of the partitioned mode (csrc/dist.cu): feb200's own NCCL communicator, created from a unique id
+    that rank 0 draws and torch.distributed broadcasts, plus one halo descriptor per RankProblem.  With it the halo-sum and
+    the whole CG loop (local SpMV, halo-sum, all-reduced dot products, vector updates) are enqueued from C on the current
+    stream; Python only polls the `done` flag between chunks of iterations."""
+
+    def __init__(self, device):
+        import ctypes
+        import torch.distributed as dist
+        lib = _lib.load()
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        idt = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (ctypes.c_uint8 * 128)()
+            if lib.feb200_nccl_unique_id(buf) != 0:
+                raise _lib.Feb200Error("feb200_nccl_unique_id failed: " + lib.feb200_last_error().decode())
+            idt = torch.tensor(list(buf), dtype=torch.uint8)
+        idt = idt.to(device)
+        dist.broadcast(idt, 0)
+        raw = bytes(idt.cpu().tolist())
+        comm = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            if lib.feb200_nccl_comm_init(self.rank, self.world, raw, ctypes.byref(comm)) != 0:
+                raise _lib.Feb200Error("feb200_nccl_comm_init failed: " + lib.feb200_last_error().decode())
+        self.comm = comm
+        self._keep = []
+
+    @staticmethod
+    def usable(comm, devices):
+        if not isinstance(comm, TorchDistComm) or comm.world < 2 or len(devices) != 1:
+            return False
+        if not torch.cuda.is_available() or torch.device(devices[0]).type != "cuda":
+            return False
+        return bool(_lib.load().feb200_nccl_available())
+
+    def halo(self, nb, U, device):
+        """feb200_halo for one rank's neighbour index sets {peer: local vertex ids (int64 tensor)}"""
+        assert len(nb) <= _lib.MAX_NEIGHBOURS, "too many neighbour ranks for the C halo descriptor"
+        h = _lib.Halo(n_neighbours=len(nb), U=U)
+        for k, p in enumerate(sorted(nb)):
+            idx = nb[p].to(torch.int64).contiguous()
+            send = torch.empty(idx.numel() * U, dtype=torch.float64, device=device)
+            recv = torch.empty_like(send)
+            self._keep.append((idx, send, recv))
+            h.peer[k], h.count[k] = p, idx.numel()
+            h.idx[k], h.send[k], h.recv[k] = _lib.ptr(idx), _lib.ptr(send), _lib.ptr(recv)
+        return h
+
+    def halo_sum(self, h, v):
+        _lib.call("feb200_halo_sum", self.comm, h, _lib.ptr(v))
+
+    def all_reduce_sum(self, t):
+        _lib.call("feb200_dot_allreduce", self.comm, _lib.ptr(t), t.numel())
 
 
 def halo_meta(nb):
@@ -213,6 +268,7 @@ class RankProblem:
             self.weights = owned.to(torch.float64).repeat_interleave(self.U).contiguous()
             self.nb = {p: torch.from_numpy(np.asarray(idx)).to(device) for p, idx in lm.neighbours.items()}
             self.idx = (lm.rank, self.nb, halo_meta(self.nb))
+            self.halo = None                      # feb200_halo, set by DistributedProblem when the C data plane is used
 
 
 class DistributedProblem:
@@ -222,6 +278,18 @@ class DistributedProblem:
         self.fj, self.comm = fj, comm
         self.token = element_residual_func
         self.rp = [RankProblem(fj, lm, make_batches, *dirichlet_local(lm), dev) for lm, dev in zip(local_meshes, devices)]
+        # C data plane (own NCCL communicator): one rank per process on a GPU, every interface vertex shared by two ranks
+        self.plane = None
+        if NcclDataPlane.usable(comm, devices) and not self.rp[0].idx[2][1]:
+            self.plane = NcclDataPlane(devices[0])
+            rp = self.rp[0]
+            rp.halo = self.plane.halo(rp.nb, rp.U, rp.device)
+
+    def _halo_sum(self, vectors):
+        if self.plane is not None:
+            self.plane.halo_sum(self.rp[0].halo, vectors[0])
+        else:
+            halo_sum(self.comm, [rp.idx for rp in self.rp], vectors, self.rp[0].U)
 
     def _each(self, fn):
         out = []
@@ -239,19 +307,20 @@ class DistributedProblem:
                 # blend fused in the element kernel; the Dirichlet residual formula must wait for the halo-sum
                 R, _ = _residual(self.token, rp.ebc, rp.maps, u, rp.mask_g, rp.values_g, fuse_dirichlet=False)
                 Rs.append(R)
-        halo_sum(self.comm, [rp.idx for rp in self.rp], Rs, self.rp[0].U)
+        self._halo_sum(Rs)
         for rp, u, R in zip(self.rp, us, Rs):
             with torch.cuda.device(rp.device):
                 _lib.call("feb200_dirichlet_residual", rp.F, _lib.ptr(u), _lib.ptr(rp.values_g), _lib.ptr(rp.mask_g), _lib.ptr(R))
         return Rs
 
     # local J_w: assembled at u_w, eliminated; unit diagonal of constrained interface DoFs kept on the owner only
-    def jacobian_w_dirichlet(self, us):
+    def jacobian_w_dirichlet(self, us, outs=None):
         from .assembly import _assemble_values
         out = []
-        for rp, u in zip(self.rp, us):
+        for i, (rp, u) in enumerate(zip(self.rp, us)):
             with torch.cuda.device(rp.device):
-                vals, pat = _assemble_values(self.token, rp.ebc, rp.maps, u, rp.mask_g, rp.values_g, eliminate=True)
+                vals, pat = _assemble_values(self.token, rp.ebc, rp.maps, u, rp.mask_g, rp.values_g,
+                                             out=None if outs is None else outs[i], eliminate=True)
                 not_owned = rp.dofs[rp.weights[rp.dofs] == 0.0]
                 if not_owned.numel():
                     self._zero_diagonal(rp, pat, vals, not_owned)
@@ -305,10 +374,22 @@ class DistributedProblem:
         idx = [rp.idx for rp in self.rp]
         U = self.rp[0].U
         if jacobi:      # diag(J_w) = halo-sum of the local diagonals
-            halo_sum(comm, idx, [s["inv_diag"] for s in sts], U)
+            self._halo_sum([s["inv_diag"] for s in sts])
             for s in sts:
                 s["inv_diag"] = (1.0 / s["inv_diag"]).contiguous()
                 s["st"].inv_diag = _lib.ptr(s["inv_diag"])
+
+        if self.plane is not None:      # the whole loop enqueued from C (csrc/dist.cu); one host sync per chunk of iterations
+            s0, rp = sts[0], self.rp[0]
+            _lib.call("feb200_cg_init_dist", self.plane.comm, s0["st"], rp.halo, float(tol), float(atol))
+            it = 0
+            while it < maxiter:
+                nit = min(poll_every, maxiter - it)
+                _lib.call("feb200_cg_iterate_dist", self.plane.comm, s0["st"], rp.halo, nit)
+                it += nit
+                if int(s0["counters"][1].item()) != 0:
+                    break
+            return [s0["x"]], int(s0["counters"][0].item()), s0["hist"][:maxiter]
 
         def stage(k, tol_=0.0, atol_=0.0):
             for rp, s in zip(self.rp, sts):
@@ -326,7 +407,7 @@ class DistributedProblem:
         stage(_lib.CG_INIT_FINALIZE)
         it = 0
         while it < maxiter:
-            for _ in range(min(poll_every, maxiter - it)):
+            for _ in range(min(poll_every, maxiter - it)):     # (finished solves: the stage kernels leave zero partials)
                 stage(_lib.CG_SPMV)                            # Ap = A_loc p and the local p.(A_loc p)
                 halo_sum(comm, idx, [s["Ap"] for s in sts], U)
                 reduce(1, 2)                                   # global p.Ap = sum over ranks of the local ones

@@ -98,6 +98,8 @@ def build_sweep_plan(vertices: torch.Tensor, conn32: torch.Tensor, row_ind: torc
                      nindptr: torch.Tensor, seg_chunks: int = SEG_CHUNKS):
     """vertices (V,3) f64, conn32 (E,8) i32, row_ind (V+1) / col_ind (E*8) int64 views of the assembly map,
     nindptr (V+1) int64 node pattern offsets."""
+    import os
+    seg_chunks = int(os.environ.get("FEB200_SWEEP_SEG", seg_chunks))
     dev = vertices.device
     V = int(vertices.shape[0])
     E, N = int(conn32.shape[0]), int(conn32.shape[1])

@@ -287,6 +287,40 @@ typedef enum { FEB200_CG_INIT_SPMV = 0, FEB200_CG_INIT_VECTORS = 1, FEB200_CG_IN
                FEB200_CG_PAP = 4, FEB200_CG_UPDATE_XR = 5, FEB200_CG_UPDATE_P = 6 } feb200_cg_stage_id;
 int feb200_cg_stage(feb200_stream s, const feb200_cg_state* st, int32_t stage, double tol, double atol);
 
+/* ------------------------------------------------------------------ element-partitioned multi-GPU data plane
+ * The reference has no distributed solver (fea.py:331-332 anticipates rank-local numbering; the only message-passing code
+ * is the mpi4py demo tests/test_mpi4py_cuda/test_mpi4py_cuda_jax_async/test_mpi4py_cuda_jax_async.py:132,229-244).  Every
+ * rank holds the sub-assembled matrix of its elements; interface rows hold partial sums.
+ * NCCL is bound at run time (dlopen of the libnccl.so.2 the host framework loaded); feb200_nccl_available() == 0 means the
+ * entry points below that take a communicator return FEB200_ERR_UNSUPPORTED. */
+#define FEB200_MAX_NEIGHBOURS 8
+typedef struct {
+    int32_t n_neighbours;                       /* ranks this rank shares vertices with, ascending rank order */
+    int32_t U;                                  /* DoFs per vertex */
+    int32_t peer[FEB200_MAX_NEIGHBOURS];
+    int32_t reserved[2];
+    int64_t count[FEB200_MAX_NEIGHBOURS];       /* shared vertices per neighbour */
+    const int64_t* idx[FEB200_MAX_NEIGHBOURS];  /* device: their local vertex ids, listed in the same order on both ranks */
+    double* send[FEB200_MAX_NEIGHBOURS];        /* device scratch, count * U doubles each */
+    double* recv[FEB200_MAX_NEIGHBOURS];
+} feb200_halo;
+int feb200_nccl_available(void);
+int feb200_nccl_unique_id(uint8_t* id128);                                   /* host: 128-byte ncclUniqueId (rank 0 creates, all ranks share it) */
+int feb200_nccl_comm_init(int32_t rank, int32_t world, const uint8_t* id128, void** comm_out);
+int feb200_nccl_comm_destroy(void* comm);
+/* send[k][i*U+j] = v[idx[k][i]*U+j]  /  v[idx[k][i]*U+j] += recv[k][i*U+j] in ascending neighbour order */
+int feb200_halo_pack(feb200_stream s, const feb200_halo* h, const double* v);
+int feb200_halo_unpack_add(feb200_stream s, const feb200_halo* h, double* v);
+/* In place: every interface DoF becomes own + the neighbours' partial values (pack, one ncclSend/ncclRecv group, add).
+ * Every interface vertex must be shared by exactly two ranks for the copies to stay bit-identical. */
+int feb200_halo_sum(feb200_stream s, void* comm, const feb200_halo* h, double* v);
+/* buf[0..n) <- sum over ranks (ncclAllReduce, in place): the CG dot products and residual norms */
+int feb200_dot_allreduce(feb200_stream s, void* comm, double* buf, int32_t n);
+/* The staged CG with the halo-sum after every local SpMV and the all-reduces of the dot products enqueued between the
+ * stages (st->weights = ownership weights); same loop and stopping test as feb200_cg_init / feb200_cg_iterate. */
+int feb200_cg_init_dist(feb200_stream s, void* comm, const feb200_cg_state* st, const feb200_halo* h, double tol, double atol);
+int feb200_cg_iterate_dist(feb200_stream s, void* comm, const feb200_cg_state* st, const feb200_halo* h, int32_t n_iters);
+
 /* Batched CG for many small systems on one mesh (vmap(cg) of the reference, solve_cg.py:20-137 under
  * tests/test_microscale_bvp.py): n_copies independent systems laid side by side, copy c owning the DoFs
  * [c*len, (c+1)*len) of every vector, the block-diagonal matrix applied with feb200_spmv.  Every copy keeps its own
