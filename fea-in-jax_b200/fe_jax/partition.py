@@ -321,20 +321,28 @@ class DistributedProblem:
             with torch.cuda.device(rp.device):
                 vals, pat = _assemble_values(self.token, rp.ebc, rp.maps, u, rp.mask_g, rp.values_g,
                                              out=None if outs is None else outs[i], eliminate=True)
-                not_owned = rp.dofs[rp.weights[rp.dofs] == 0.0]
-                if not_owned.numel():
-                    self._zero_diagonal(rp, pat, vals, not_owned)
+                pos = self._not_owned_diagonal(rp, pat)
+                if pos is not None:
+                    vals[pos] = 0.0
                 out.append(vals)
         return out
 
     @staticmethod
-    def _zero_diagonal(rp, pat, vals, dofs):
-        a = dofs // pat.U
-        i = dofs - a * pat.U
-        p0 = pat.nindptr[a]
-        deg = pat.nindptr[a + 1] - p0
-        pos = pat.U * pat.U * p0 + i * pat.U * deg + pat.U * pat.diag_rank[a].to(torch.int64) + i
-        vals[pos] = 0.0
+    def _not_owned_diagonal(rp, pat):
+        """CSR positions of the unit diagonals of constrained interface DoFs this rank does not own (computed once per
+        pattern: no host synchronisation on the assembly path)."""
+        hit = getattr(rp, "_nod", None)
+        if hit is None or hit[0] is not pat:
+            dofs = rp.dofs[rp.weights[rp.dofs] == 0.0]
+            pos = None
+            if dofs.numel():
+                a = dofs // pat.U
+                i = dofs - a * pat.U
+                p0 = pat.nindptr[a]
+                deg = pat.nindptr[a + 1] - p0
+                pos = (pat.U * pat.U * p0 + i * pat.U * deg + pat.U * pat.diag_rank[a].to(torch.int64) + i).contiguous()
+            rp._nod = hit = (pat, pos)
+        return hit[1]
 
     def norm(self, vs):
         parts = []

@@ -463,6 +463,62 @@ def test_full_size_hex8_properties(fj, n):
     assert torch.equal(J.data, J2.data)
 
 
+def test_benched_configuration_matches_oracle_at_64(fj):
+    """The configuration bench.py times -- jittered hex8 grid, per-point Young's modulus (E,Q,2) with one Poisson ratio (the
+    streaming fused kernel with FEB200_HINT_UNIFORM_POISSON), Dirichlet faces -- at 64^3 (262 144 elements, 64.7 M non-zeros),
+    the largest size the oracle's element tangents + a host-side duplicate sum handle in about a minute: residual with
+    Dirichlet, CSR values of J and of J_w against the oracle (fea.py:613-660, :922-965, sparse_matrix.py:157-184)."""
+    import scipy.sparse as sp
+    import bench
+    from fe_jax import _lib
+    n = 64
+    Vx, cells, mp = bench.make_problem(n, n, "EQM")
+    E, V = cells.shape[0], Vx.shape[0]
+    F = 3 * V
+    fe = fj.FiniteElementType(fj.CellType.hexahedron, fj.ElementFamily.P, 1, fj.LagrangeVariant.equispaced,
+                              fj.QuadratureType.default, 2)
+    batch = fj.ElementBatch(fe_type=fe, n_dofs_per_basis=3, connectivity_en=cells, constitutive_model=fj.elastic_isotropic,
+                            material_params=mp)
+    ebc = fj.batch_to_collection(Vx, [batch])
+    maps = [fj.mesh_to_sparse_assembly_map(V, cells)]
+    left, right = np.nonzero(Vx[:, 0] < 1e-12)[0], np.nonzero(Vx[:, 0] > 1 - 1e-12)[0]
+    dofs = np.concatenate([3 * left, 3 * left + 1, 3 * left + 2, 3 * right])
+    mask = np.zeros(F); mask[dofs] = 1.0
+    vals = np.zeros(F); vals[3 * right] = 0.01
+    u = 1e-3 * np.random.default_rng(1).uniform(size=F)
+    before = dict(_lib.launches_by_name)
+    R, _ = fj.calculate_residual_w_dirichlet(fj.linear_elasticity_residual, ebc, maps, u, vals, mask)
+    nnz = fj._calculate_jacobian_unique_nnz(V, ebc)
+    assert nnz == 9 * (3 * n + 1) ** 3
+    J = fj.calculate_jacobian_wo_dirichlet(fj.linear_elasticity_residual, ebc, maps, u, nnz)
+    Jw = fj.calculate_jacobian_w_dirichlet(fj.linear_elasticity_residual, ebc, maps, u, vals, mask, nnz)
+    assert _lib.launches_by_name.get("feb200_assemble_fused_hex8_sweep", 0) - before.get("feb200_assemble_fused_hex8_sweep", 0) == 2
+    # oracle: residual, element tangents, duplicate sum on the host (scipy sums the COO triples of fea.py:592-594)
+    xi, W = orc.get_quadrature("hexahedron", 2)
+    _, dphi = orc.eval_basis_and_derivatives("hexahedron", 1, xi)
+    prob = orc.Problem(Vx, [orc.Batch(cells, "linear", "elastic_isotropic", mp, dphi, W)])
+    R_o = prob.residual_w_dirichlet(u, vals, mask)
+    assert rel_err(R, R_o) <= ASM_RTOL
+    Ke = orc.element_tangents("linear", "elastic_isotropic", np.zeros((E, 8, 3)), Vx[cells], dphi, orc.weights_as_reference(W),
+                              orc.expand_material(mp, E, 8))
+    dof = orc.get_dof_map(cells, 3).astype(np.int32)
+    rows = np.repeat(dof, 24, axis=1).reshape(-1)
+    cols = np.tile(dof, (1, 24)).reshape(-1)
+    A = sp.coo_matrix((Ke.reshape(-1), (rows, cols)), shape=(F, F)).tocsr()
+    del Ke, rows, cols
+    A.sum_duplicates(); A.sort_indices()
+    row_g, col_g = np_(J.row), np_(J.col)
+    # scipy keeps structural zeros as explicit entries, so its sorted CSR is the reference's sorted-unique (row, col) order
+    assert A.nnz == nnz and np.array_equal(A.indices, col_g)
+    assert np.array_equal(A.indptr[1:], np.cumsum(np.bincount(row_g, minlength=F)))
+    d_o = A.data
+    assert rel_err(J.data, d_o) <= ASM_RTOL
+    elim = (mask[row_g] != 0) | (mask[col_g] != 0)
+    dw_o = np.where(elim, np.where((row_g == col_g) & (mask[row_g] != 0), 1.0, 0.0), d_o)
+    assert rel_err(Jw.data, dw_o) <= ASM_RTOL
+    assert np.array_equal(np_(Jw.data)[elim], dw_o[elim])    # eliminated entries are exact zeros and ones
+
+
 # ------------------------------------------------------------------------------------------ fused assembly kernel
 @pytest.mark.parametrize("n,layout,shuffle", [(5, "M", False), (7, "EM", False), (6, "M", True), (9, "EM", True),
                                               (6, "EQM", False), (8, "EQM", True)])

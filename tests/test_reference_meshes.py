@@ -135,3 +135,35 @@ def test_batched_rve_solves_match_individual_solves(fj):
         assert rel_err(u_b[c], u1.cpu().numpy()) <= 1e-7
         k1 = int(fj.solve_bvp.last_info.linear_iterations_per_nonlinear_iteration[0])
         assert abs(int(k_b[c]) - k1) <= 1, (c, int(k_b[c]), k1)     # same iteration as the stand-alone solve (vmap semantics)
+
+
+@pytest.mark.gpu
+def test_batched_rve_solves_match_the_oracle_per_copy(fj):
+    """Config 5 against the oracle (not against the GPU itself): 64 copies of a quad4 RVE with per-copy modulus fields and
+    boundary values through solve_bvp_batched; six of them are solved one by one by orc.solve_bvp (the reference's Newton
+    + CG, fea.py:1132-1309 / solve_cg.py:20-63) and must agree to the solver tolerance, iteration counts included."""
+    V3, cells = fj.uniform_quad_grid(7, 7, np.array([[0.0, 1.0], [0.0, 1.0]]))
+    pts = V3[:, :2]
+    C, E = 64, cells.shape[0]
+    rng = np.random.default_rng(5)
+    mp = np.empty((C, E, 4, 2))
+    mp[..., 0] = 10e9 + 90e9 * rng.uniform(size=(C, E, 4))
+    mp[..., 1] = 0.25
+    edge = np.nonzero((pts[:, 0] < 1e-12) | (pts[:, 0] > 1 - 1e-12))[0]
+    bcs = np.stack([np.repeat(edge, 2), np.tile([0, 1], edge.shape[0])], axis=1)
+    vals = 1e-3 * rng.uniform(size=(C, bcs.shape[0]))
+    fe = fj.FiniteElementType(fj.CellType.quadrilateral, fj.ElementFamily.P, 1, fj.LagrangeVariant.equispaced,
+                              fj.QuadratureType.default, 2)
+    batch = fj.ElementBatch(fe_type=fe, n_dofs_per_basis=2, connectivity_en=cells, constitutive_model=fj.elastic_isotropic,
+                            material_params=mp[0])
+    opts = fj.SolverOptions(linear_precond_type=fj.PreconditionerType.JACOBI, linear_max_iter=4000)
+    u_b, res_b = fj.solve_bvp_batched(pts, [batch], fj.linear_elasticity_residual, bcs, vals, [mp], solver_options=opts)
+    k_b = fj.solve_bvp_batched.last_iterations[0]
+    xi, W = orc.get_quadrature("quadrilateral", 2)
+    _, dphi = orc.eval_basis_and_derivatives("quadrilateral", 1, xi)
+    for c in (0, 7, 21, 40, 55, 63):
+        ob = [orc.Batch(cells, "linear", "elastic_isotropic", mp[c], dphi, W)]
+        u_o, R_o, info = orc.solve_bvp(pts, ob, None, bcs, vals[c], options={"precond": "JACOBI", "linear_max_iter": 4000})
+        assert rel_err(u_b[c], u_o) <= 1e-7, c
+        k_o = int(info["linear_iterations_per_nonlinear_iteration"][0])
+        assert abs(int(k_b[c]) - k_o) <= 2, (c, int(k_b[c]), k_o)
