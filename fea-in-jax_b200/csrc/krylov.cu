@@ -618,9 +618,15 @@ static bool spmv_bulk_enabled() {
 static int spmv_dispatch(cudaStream_t st, int64_t V, int U, const int64_t* nindptr, const int32_t* nindices,
                          const double* values, const double* x, double* y, double* dot_out, ReduceWs ws,
                          const int32_t* counters, double* scalars) {
-    if (U == 3 && spmv_bulk_enabled()) {
+    // the bulk copies read 16-byte aligned pieces of `values`: any other base address (a tensor view, an XLA sub-buffer)
+    // takes the plain-load kernel instead of faulting
+    if (U == 3 && spmv_bulk_enabled() && ((uintptr_t)values & 15u) == 0) {
         const size_t smem = (size_t)SPB_WARPS * SPB_NB * SPB_BUF_BYTES;
-        FEB_CUDA(cudaFuncSetAttribute(k_spmv3_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        static bool attr_set = false;
+        if (!attr_set) {
+            FEB_CUDA(cudaFuncSetAttribute(k_spmv3_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
         int64_t g = ceil_div(ceil_div(V, SPB_CH), SPB_WARPS);
         int64_t cap = (int64_t)sm_count() * FEB_SPMV_CTAS;
         if (dot_out || scalars) cap = MAX_PARTIALS < cap ? MAX_PARTIALS : cap;

@@ -2,11 +2,14 @@
 //
 // NOT compiled in this image: jax / jaxlib (and therefore xla/ffi/api/ffi.h, found through
 // jax.ffi.include_dir()) are not installable here.  Build where JAX exists with
-//   g++ -std=c++17 -shared -fPIC -I$(python -c "import jax.ffi; print(jax.ffi.include_dir())") \
-//       -Iinclude fea-in-jax_b200/csrc/xla_ffi_shim.cc -L fea-in-jax_b200/lib -lfeb200 -o libfeb200_xla.so
+//   g++ -std=c++17 -shared -fPIC -I$(python -c "import jax.ffi; print(jax.ffi.include_dir())") -I/usr/local/cuda/include \
+//       -Iinclude fea-in-jax_b200/csrc/xla_ffi_shim.cc -L fea-in-jax_b200/lib -lfeb200 -L/usr/local/cuda/lib64 -lcudart \
+//       -o libfeb200_xla.so
 // Each handler only forwards XLA's stream and buffers: XLA owns all operand / result buffers, the
 // handler enqueues on the given stream and returns (no sync, no allocation => usable inside
 // lax.while_loop and CUDA-graph capture).  See INTEGRATION.md for the Python registration.
+#include <cuda_runtime.h>
+
 #include "xla/ffi/api/ffi.h"
 
 #include "feb200.h"
@@ -15,6 +18,10 @@ namespace ffi = xla::ffi;
 
 static ffi::Error status(int rc) {
     return rc == 0 ? ffi::Error::Success() : ffi::Error(ffi::ErrorCode::kInternal, feb200_last_error());
+}
+// optional operands (Dirichlet mask / values): a zero-size buffer stands for "not given"
+template <typename B> static auto opt_data(const B& b) -> decltype(b.typed_data()) {
+    return b.element_count() == 0 ? nullptr : b.typed_data();
 }
 
 // y = A x on the node-pattern CSR (replaces the JVP operator of sparse_linear_solve.py:251-258)
@@ -60,8 +67,8 @@ static ffi::Error ResidualImpl(cudaStream_t stream, ffi::Buffer<ffi::S32> conn, 
                                ffi::Buffer<ffi::F64> u, ffi::Buffer<ffi::F64> mask, ffi::Buffer<ffi::F64> values,
                                ffi::ResultBuffer<ffi::F64> R_e, int64_t kind, int64_t material, int64_t layout) {
     const feb200_batch b = make_batch(conn, dphi, W, mp, kind, material, layout);
-    return status(feb200_element_residual(stream, &b, x_vd.typed_data(), u.typed_data(), mask.typed_data(),
-                                          values.typed_data(), R_e->typed_data()));
+    return status(feb200_element_residual(stream, &b, x_vd.typed_data(), u.typed_data(), opt_data(mask),
+                                          opt_data(values), R_e->typed_data()));
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(feb200_xla_element_residual, ResidualImpl,
                               ffi::Ffi::Bind()
@@ -84,7 +91,7 @@ static ffi::Error ScatterSumImpl(cudaStream_t stream, ffi::Buffer<ffi::U64> row_
                                  ffi::Buffer<ffi::F64> u, ffi::ResultBuffer<ffi::F64> R, int64_t U) {
     const int64_t V = row_ind.element_count() - 1;
     return status(feb200_scatter_sum(stream, row_ind.typed_data(), col_ind.typed_data(), V, (int32_t)U, R_e.typed_data(),
-                                     R->typed_data(), 0, mask.typed_data(), values.typed_data(), u.typed_data()));
+                                     R->typed_data(), 0, opt_data(mask), opt_data(values), opt_data(u)));
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(feb200_xla_scatter_sum, ScatterSumImpl,
                               ffi::Ffi::Bind()
@@ -157,8 +164,8 @@ static ffi::Error TangentImpl(cudaStream_t stream, ffi::Buffer<ffi::S32> conn, f
                               ffi::Buffer<ffi::F64> u, ffi::Buffer<ffi::F64> mask, ffi::Buffer<ffi::F64> values,
                               ffi::ResultBuffer<ffi::F64> K_e, int64_t kind, int64_t material, int64_t layout) {
     const feb200_batch b = make_batch(conn, dphi, W, mp, kind, material, layout);
-    return status(feb200_element_tangent(stream, &b, x_vd.typed_data(), u.typed_data(), mask.typed_data(),
-                                         values.typed_data(), K_e->typed_data()));
+    return status(feb200_element_tangent(stream, &b, x_vd.typed_data(), u.typed_data(), opt_data(mask),
+                                         opt_data(values), K_e->typed_data()));
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(feb200_xla_element_tangent, TangentImpl,
                               ffi::Ffi::Bind()
@@ -189,8 +196,8 @@ static ffi::Error AssembleCsrImpl(cudaStream_t stream, ffi::Buffer<ffi::S32> con
     m.col_ind = col_ind.typed_data();
     const int64_t V = nindptr.element_count() - 1;
     return status(feb200_assemble_csr(stream, &m, V, (int32_t)U, K_e.typed_data(), slot_rank.typed_data(),
-                                      nindptr.typed_data(), (int32_t)max_deg, values->typed_data(), 0, nindices.typed_data(),
-                                      mask.typed_data()));
+                                      nindptr.typed_data(), (int32_t)max_deg, values->typed_data(), 0,
+                                      mask.element_count() ? nindices.typed_data() : nullptr, opt_data(mask)));
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(feb200_xla_assemble_csr, AssembleCsrImpl,
                               ffi::Ffi::Bind()
@@ -235,7 +242,15 @@ static ffi::Error CgImpl(cudaStream_t stream, ffi::Buffer<ffi::S64> nindptr, ffi
     st.counters = counters->typed_data();
     st.ws = ws->typed_data();
     st.ws_bytes = ws->element_count();
-    cudaMemcpyAsync(st.x, x0.typed_data(), sizeof(double) * x0.element_count(), cudaMemcpyDeviceToDevice, stream);
+    if (cudaMemcpyAsync(st.x, x0.typed_data(), sizeof(double) * x0.element_count(), cudaMemcpyDeviceToDevice, stream) !=
+        cudaSuccess)
+        return ffi::Error(ffi::ErrorCode::kInternal, "feb200_xla_cg: copy of x0 failed");
+    // `maxiter` is the number of iterations ENQUEUED (kernels exit at once when the device-side `done` flag is set, 3-4
+    // launches each): the caller passes an explicit bound -- sparse_linear_solve.py:106 caps CG at 1000 -- and, for longer
+    // solves, calls the handler again from a lax.while_loop on the returned `counters` (k, done) instead of enqueueing
+    // the 10*n iterations of the CG_JAX_SCIPY default in one go.
+    if (maxiter < 0 || maxiter > 4096)
+        return ffi::Error(ffi::ErrorCode::kInvalidArgument, "feb200_xla_cg: maxiter must be in [0, 4096] per call");
     int rc = feb200_cg_init(stream, &st, tol, atol);
     if (rc == 0) rc = feb200_cg_iterate(stream, &st, (int32_t)maxiter);
     return status(rc);

@@ -162,6 +162,9 @@ class ElementBatchCollection:
         model = resolve_model(self.constitutive_models[i])
         if model.kind != kind:
             raise _lib.Feb200Error(f"constitutive model {model.__name__} cannot be used with this element residual")
+        if self.U[i] != self.D:
+            raise _lib.Feb200Error(f"batch {i}: n_dofs_per_basis={self.U[i]} but the element kernels write D={self.D} components "
+                                   "per node (the reference assumes U == D too, fea.py:550)")
         mp = self.get_material_params(i)
         need = model.n_params(self.D)
         if self.M[i] < need:
