@@ -52,6 +52,7 @@ def parse():
                     help="hyper = BASELINE configs[2]: hyperelastic (St. Venant-Kirchhoff) residual and tangent, generic two-pass "
                          "assembly; the CPU baseline legs stay on the linear workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-solve", action="store_true", help="N = 1: skip the converged Jacobi-CG / multigrid-CG solves")
     ap.add_argument("--no-hyper", action="store_true", help="skip the hyperelastic (BASELINE configs[2]) Newton-CG block")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the partitioned-vs-single-GPU parity solve")
     ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the secondary weak-scaling block")
@@ -435,6 +436,37 @@ def main():
                               + ("linear_solve" if world == 1 else "the element-partitioned driver (halo-sum after each local SpMV / "
                                  "scatter, all-reduced CG scalars)"))
 
+    # ---- converged solve of the Newton system (relative residual 1e-8): the reference's Jacobi-CG configuration against CG
+    #      preconditioned by fe_jax.GeometricMultigrid (iterations and time to solution; N = 1, linear workload)
+    solve_block = None
+    if world == 1 and not hyper_main and not args.no_solve:
+        R0 = run.assembly_step()
+        Jc = fj.COO((J_vals,), shape=(F, F), rows_sorted=True, pattern=pat)
+        b_rhs = (-R0).contiguous()
+        x0 = torch.zeros_like(b_rhs)
+        x0[run.dofs] = run.dvals - u[run.dofs]
+
+        def wall(fn):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = fn()
+            torch.cuda.synchronize()
+            return out, time.perf_counter() - t0
+
+        (xj, ij), tj = wall(lambda: fj.cg(Jc, b_rhs, x0, tol=1e-8, maxiter=20000,
+                                          M=fj.JacobiPreconditioner(csr_diagonal(pat, J_vals))))
+        young = pr.mp[..., 0] if pr.mp.ndim > 1 else float(pr.mp[0])
+        mg, t_setup_mg = wall(lambda: fj.GeometricMultigrid(pr.Vx, (n, n, n), young, 0.25, mask, pat, J_vals))
+        (xm, im), tm = wall(lambda: fj.cg(Jc, b_rhs, x0, tol=1e-8, maxiter=500, M=mg))
+        solve_block = {"relative_tolerance": 1e-8,
+                       "jacobi_cg": {"iterations": int(ij["iterations"]), "solve_s": tj},
+                       "multigrid_cg": {"iterations": int(im["iterations"]), "solve_s": tm, "setup_s": t_setup_mg,
+                                        "levels": [list(g) for g in mg.shape_summary]},
+                       "solutions_max_rel_diff": float(((xj - xm).abs().max() / xj.abs().max()).item()),
+                       "note": "Jacobi = the reference's only preconditioner (sparse_linear_solve.py:301-306); multigrid = "
+                               "fe_jax.GeometricMultigrid (re-discretised coarse levels, Chebyshev smoothing)"}
+        del mg, xj, xm, Jc
+
     # ---- end to end through the public API with host buffers
     copy_stream = torch.cuda.Stream(device=dev)
     r_ready, u_ready, j_ready = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
@@ -574,6 +606,8 @@ def main():
             "clocks": clocks,
         }
         line.update(extra)
+        if solve_block is not None:
+            line["solve_to_tolerance"] = solve_block
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_block(args, fj, _lib, torch, dev)
         emit(line)

@@ -25,8 +25,9 @@ from .sparse import (coo_arrays_sum_duplicates, coo_arrays_sum_duplicates_jit, c
 from .krylov import cg, JacobiPreconditioner
 from .krylov import cg as cg_w_info
 from .solver import (PreconditionerType, LinearSolverType, SolverOptions, SolverResultInfo, init_solver_info,
-                     Residual, Jacobian, JacobianDiagonl, linear_solve)
+                     Residual, Jacobian, JacobianDiagonl, linear_solve, set_multigrid_factory)
 from .newton import solve_nonlinear_step, solve_bvp
 from . import partition
 from .vtk_io import read_vtk, write_vtk
 from .batched import solve_bvp_batched
+from .multigrid import GeometricMultigrid

@@ -123,6 +123,8 @@ SIGNATURES = {
     "feb200_cg_iterate_dist": (c_int32, [_P, _P, POINTER(CGState), POINTER(Halo), _I32]),
     "feb200_bcg_init": (c_int32, [_P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _F64, _F64, _I32]),
     "feb200_bcg_step": (c_int32, [_P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _I32]),
+    "feb200_mg_prolong_add": (c_int32, [_P, _I32, _I32, _I32, _I32, _P, _P, _P]),
+    "feb200_mg_restrict": (c_int32, [_P, _I32, _I32, _I32, _I32, _P, _P, _P]),
     "feb200_axpby": (c_int32, [_P, _I64, _F64, _P, _F64, _P, _P]),
     "feb200_scatter_set": (c_int32, [_P, _I64, _P, _P, _F64, _P, _P]),
 }

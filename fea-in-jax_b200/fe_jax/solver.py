@@ -28,6 +28,7 @@ class PreconditionerType(Enum):
     NONE = auto()
     JACOBI = auto()
     ILU_CUPY = auto()
+    GEOMETRIC_MULTIGRID = auto()   # not in the reference (it reaches for AMGX, sparse_linear_solve.py:704-729): fe_jax.multigrid
 
 
 class LinearSolverType(Enum):
@@ -157,6 +158,17 @@ def linear_solve(residual: Residual, jacobian: Optional[Jacobian], jacobian_diag
             f"{solver_options.linear_precond_type} requires the `jacobian_diagonal` argument to be provided."
         from .assembly import csr_diagonal
         inv_diag = JacobiPreconditioner(csr_diagonal(pat, J.data)).inv_diag     # diag of the eliminated matrix
+    elif solver_options.linear_precond_type == PreconditionerType.GEOMETRIC_MULTIGRID:
+        if _MULTIGRID["factory"] is None:
+            raise _lib.Feb200Error("PreconditionerType.GEOMETRIC_MULTIGRID needs set_multigrid_factory(lambda J: "
+                                   "GeometricMultigrid(...)) first (the grid shape is not part of the reference call surface)")
+        from .krylov import cg as _cg
+        M = _MULTIGRID["factory"](J)
+        b = (-R_0).contiguous()
+        delta_x, cg_info = _cg(J, b, delta_x, tol=solver_options.linear_relative_tol, atol=solver_options.linear_absolute_tol,
+                               maxiter=solver_options.linear_max_iter, M=M)
+        k, hist = int(cg_info["iterations"]), cg_info["residual_norm_history"]
+        return _finish(delta_x, k, hist, dofs, values, x_0, solver_options, solver_info_0)
     elif solver_options.linear_precond_type != PreconditionerType.NONE:
         raise Exception(f"Preconditioner type {solver_options.linear_precond_type} is not implemented")
 
@@ -172,6 +184,19 @@ def linear_solve(residual: Residual, jacobian: Optional[Jacobian], jacobian_diag
     else:
         delta_x, k, hist = cg_on_pattern(pat, J.data, b, delta_x, solver_options.linear_relative_tol,
                                          solver_options.linear_absolute_tol, maxiter, inv_diag)
+    return _finish(delta_x, k, hist, dofs, values, x_0, solver_options, solver_info_0)
+
+
+_MULTIGRID = {"factory": None}
+
+
+def set_multigrid_factory(factory):
+    """factory(J: COO on a NodePattern) -> preconditioner callable, used by PreconditionerType.GEOMETRIC_MULTIGRID
+    (None removes it)."""
+    _MULTIGRID["factory"] = factory
+
+
+def _finish(delta_x, k, hist, dofs, values, x_0, solver_options, solver_info_0):
     info = solver_info_0
     if solver_options.linear_solve_type == LinearSolverType.CG_JAX_SCIPY_W_INFO:
         per_nl = solver_info_0.linear_iterations_per_nonlinear_iteration.clone()

@@ -334,6 +334,16 @@ int feb200_bcg_init(feb200_stream s, int64_t n_copies, int64_t len, const double
 int feb200_bcg_step(feb200_stream s, int64_t n_copies, int64_t len, const double* Ap, const double* inv_diag, double* x,
                     double* r, double* p, double* scal, int32_t* cnt, double* hist, int32_t maxiter);
 
+/* ------------------------------------------------------------------ geometric multigrid transfers (structured hex8 grids)
+ * Stronger preconditioner than the reference's Jacobi (sparse_linear_solve.py:301-306; the reference reaches for AMGX,
+ * :704-729).  Vertex id = (i*(ny+1) + j)*(nz+1) + k, U DoFs per vertex; the fine grid has (2 nxc, 2 nyc, 2 nzc) elements.
+ * prolong_add: fine += P coarse (trilinear), skipping entries with mask_fine != 0;  restrict: coarse = P^T fine with
+ * entries with mask_coarse != 0 set to zero.  Masks may be NULL. */
+int feb200_mg_prolong_add(feb200_stream s, int32_t nxc, int32_t nyc, int32_t nzc, int32_t U, const double* coarse,
+                          const double* mask_fine, double* fine);
+int feb200_mg_restrict(feb200_stream s, int32_t nxc, int32_t nyc, int32_t nzc, int32_t U, const double* fine,
+                       const double* mask_coarse, double* coarse);
+
 /* fused vector helpers used by linear_solve / Newton (sparse_linear_solve.py:287-292, 527; fea.py:1103) */
 int feb200_axpby(feb200_stream s, int64_t n, double a, const double* x, double b, const double* y, double* out);
 int feb200_scatter_set(feb200_stream s, int64_t n_idx, const int64_t* idx, const double* vals, double scale_vals,
