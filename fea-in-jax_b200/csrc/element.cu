@@ -452,6 +452,34 @@ __global__ void k_tangent_general_rt(feb200_batch b, int epb, int per_el, const 
     }
 }
 
+// diag(K_e) of the linear isotropic law without forming K_e: K[(a,d),(a,d)] = sum_q w (lam* g_ad^2 + mu g_ad^2 + mu |g_a|^2)
+// (SURVEY appendix A.2 with a = b, d = k; calculate_jacobian_diag_wo_dirichlet, fea.py:759-797).  Thread per element.
+template <int D>
+__global__ void __launch_bounds__(128) k_tangent_diag_iso(feb200_batch b, const double* __restrict__ x_vd, double* __restrict__ diag_e) {
+    const int N = b.N;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < b.E; e += (int64_t)gridDim.x * blockDim.x) {
+        double x[MAX_RT_N * D], g[MAX_RT_N * D], acc[MAX_RT_N * D];
+        for (int n = 0; n < N; ++n) {
+            const int64_t v = b.conn[e * N + n];
+            for (int d = 0; d < D; ++d) { x[n * D + d] = x_vd[v * D + d]; acc[n * D + d] = 0.0; }
+        }
+        int qs;
+        const double* mp = mp_of(b, e, qs);
+        for (int q = 0; q < b.Q; ++q) {
+            const double dt = shape_gradients_rt<D>(N, x, b.dphi + (int64_t)q * N * D, g);
+            double lam, mu;
+            isotropic_lame<D>(mp + (int64_t)q * qs, lam, mu);
+            const double w = dt * b.W[q];
+            for (int n = 0; n < N; ++n) {
+                double g2 = 0.0;
+                for (int d = 0; d < D; ++d) g2 += g[n * D + d] * g[n * D + d];
+                for (int d = 0; d < D; ++d) acc[n * D + d] += w * ((lam + mu) * g[n * D + d] * g[n * D + d] + mu * g2);
+            }
+        }
+        for (int i = 0; i < N * D; ++i) diag_e[e * N * D + i] = acc[i];
+    }
+}
+
 static int check_batch(const feb200_batch* b, const char* who) {
     FEB_REQUIRE(b, FEB200_ERR_INVALID, "%s: null batch", who);
     FEB_REQUIRE(b->E >= 0 && b->N > 0 && b->Q > 0 && (b->D == 2 || b->D == 3), FEB200_ERR_INVALID,
@@ -589,6 +617,20 @@ int feb200_element_tangent(feb200_stream s, const feb200_batch* bp, const double
 #undef FEB_TANGENT_CASE
     if (rc) return rc;
     FEB_CHECK_LAUNCH("element_tangent");
+    return FEB200_OK;
+}
+
+int feb200_element_tangent_diag(feb200_stream s, const feb200_batch* bp, const double* x_vd, double* diag_e) {
+    int rc = check_batch(bp, "element_tangent_diag");
+    if (rc) return rc;
+    FEB_REQUIRE(x_vd && diag_e, FEB200_ERR_INVALID, "element_tangent_diag: null pointer");
+    FEB_REQUIRE(bp->kind == KIND_LINEAR && bp->material == MAT_ISOTROPIC, FEB200_ERR_UNSUPPORTED,
+                "element_tangent_diag: only the linear isotropic law has a diagonal-only kernel");
+    if (bp->E == 0) return FEB200_OK;
+    const int grid = grid_for(bp->E, 128);
+    if (bp->D == 3) k_tangent_diag_iso<3><<<grid, 128, 0, as_stream(s)>>>(*bp, x_vd, diag_e);
+    else k_tangent_diag_iso<2><<<grid, 128, 0, as_stream(s)>>>(*bp, x_vd, diag_e);
+    FEB_CHECK_LAUNCH("element_tangent_diag");
     return FEB200_OK;
 }
 

@@ -83,6 +83,7 @@ SIGNATURES = {
     "feb200_dirichlet_residual": (c_int32, [_P, _I64, _P, _P, _P, _P]),
     "feb200_element_residual": (c_int32, [_P, POINTER(Batch), _P, _P, _P, _P, _P]),
     "feb200_element_tangent": (c_int32, [_P, POINTER(Batch), _P, _P, _P, _P, _P]),
+    "feb200_element_tangent_diag": (c_int32, [_P, POINTER(Batch), _P, _P]),
     "feb200_pattern_count": (c_int32, [_P, POINTER(BatchMap), _I32, _I64, _P, _P]),
     "feb200_scan_workspace_bytes": (_SZ, [_I64]),
     "feb200_pattern_scan": (c_int32, [_P, _P, _I64, _P, _P, _SZ]),

@@ -533,8 +533,22 @@ def calculate_jacobian_w_dirichlet(element_residual_func, ebc: ElementBatchColle
 
 
 def calculate_jacobian_diag_wo_dirichlet(element_residual_func, ebc: ElementBatchCollection, assembly_map_b, u_f):
-    """diag(J) (F,) (fea.py:759-797) -- read off the deterministically assembled CSR."""
+    """diag(J) (F,) (fea.py:759-797).  Linear isotropic batches: element diagonals from a diagonal-only kernel, scatter-summed
+    in ascending slot order (no matrix is assembled); anything else: read off the deterministically assembled CSR."""
     u = _as_u(ebc, u_f)
+    res = resolve_residual(element_residual_func)
+    structs = [ebc._batch_struct(i, res.kind) for i in range(ebc.B)]
+    if all(b.kind == _lib.KIND_LINEAR and b.material == _lib.MAT_ISOTROPIC for b in structs):
+        diag = torch.empty(u.shape[0], dtype=torch.float64, device=u.device)
+        for i, b in enumerate(structs):
+            d_e = ebc._buffer("R_e", ebc.E[i] * ebc.N[i] * ebc.U[i])
+            _lib.call("feb200_element_tangent_diag", b, _lib.ptr(ebc._vertices), _lib.ptr(d_e))
+            am = assembly_map_b[i]
+            row = am.indptr.reshape(-1).view(torch.int64)
+            col = am.indices.reshape(-1).view(torch.int64)
+            _lib.call("feb200_scatter_sum", _lib.ptr(row), _lib.ptr(col), am.shape[1], ebc.U[i], _lib.ptr(d_e), _lib.ptr(diag),
+                      1 if i > 0 else 0, None, None, None)
+        return diag
     vals, pat = _assemble_values(element_residual_func, ebc, assembly_map_b, u)
     return csr_diagonal(pat, vals)
 

@@ -107,6 +107,11 @@ int feb200_element_residual(feb200_stream s, const feb200_batch* b, const double
 int feb200_element_tangent(feb200_stream s, const feb200_batch* b, const double* x_vd, const double* u,
                            const double* mask, const double* values, double* K_e);
 
+/* diag_e (E, N, D): diagonal of the element tangent of the linear isotropic law, K_e never formed; scatter-summed by the
+ * caller it is calculate_jacobian_diag_wo_dirichlet (fea.py:759-797) without assembling the matrix.  Other laws:
+ * FEB200_ERR_UNSUPPORTED (the caller reads the diagonal off the assembled CSR instead). */
+int feb200_element_tangent_diag(feb200_stream s, const feb200_batch* b, const double* x_vd, double* diag_e);
+
 /* ------------------------------------------------------------------ Jacobian sparsity (fea.py:490-516)
  * The pattern is held at NODE level: nindptr (V+1) int64, nindices (nnz_nodes) int32 = sorted unique
  * neighbour list of each vertex over all batches.  The DoF-level CSR the reference produces
