@@ -100,6 +100,11 @@ def build_sweep_plan(vertices: torch.Tensor, conn32: torch.Tensor, row_ind: torc
     nindptr (V+1) int64 node pattern offsets."""
     import os
     seg_chunks = int(os.environ.get("FEB200_SWEEP_SEG", seg_chunks))
+    if vertices.is_cuda and "FEB200_SWEEP_SEG" not in os.environ:
+        # small meshes (one slab of a partitioned run): shorter segments so that every worker (warp) still gets about a
+        # dozen of them -- with 5 segments per warp the round-robin assignment left 18 % of the workers one segment short
+        workers = torch.cuda.get_device_properties(vertices.device).multi_processor_count * 8
+        seg_chunks = max(8, min(seg_chunks, int(vertices.shape[0] / 4 / (12 * workers)) or 8))
     dev = vertices.device
     V = int(vertices.shape[0])
     E, N = int(conn32.shape[0]), int(conn32.shape[1])
