@@ -26,16 +26,26 @@ SEG_CHUNKS = 48
 
 
 def _quantise(vertices: torch.Tensor) -> torch.Tensor:
-    """integer grid coordinates of every vertex on a grid whose cell is the mean vertex spacing (exact for jittered
-    uniform grids with a jitter below half a cell)"""
+    """integer grid coordinates of every vertex on the lattice a uniform grid with this bounding box and vertex count
+    would have: the spacing h solves prod_a (ext_a / h + 1) = V, which is exact for (jittered) uniform grids of any aspect
+    ratio (jitter below half a cell) and a reasonable binning for anything else"""
     V, D = vertices.shape
     lo = vertices.min(dim=0).values
     hi = vertices.max(dim=0).values
-    ext = torch.clamp(hi - lo, min=1e-300)
-    vol = float(torch.prod(ext).item())
-    cell = (vol / max(V, 1)) ** (1.0 / D)
-    counts = torch.clamp(torch.round(ext / cell), min=2.0)
-    spacing = ext / (counts - 1.0)
+    ext = [max(float(e), 1e-300) for e in (hi - lo).tolist()]
+    a, b = 1e-12 * max(ext), 2.0 * max(ext)                   # bisection on h: the product decreases monotonically in h
+    for _ in range(200):
+        h = 0.5 * (a + b)
+        prod = 1.0
+        for e in ext:
+            prod *= e / h + 1.0
+        if prod > V:
+            a = h
+        else:
+            b = h
+    h = 0.5 * (a + b)
+    counts = torch.tensor([max(round(e / h) + 1, 2) for e in ext], dtype=torch.float64, device=vertices.device)
+    spacing = torch.tensor(ext, dtype=torch.float64, device=vertices.device) / (counts - 1.0)
     return torch.floor((vertices - lo) / spacing + 0.5).to(torch.int64).clamp_(0, (1 << 20) - 1)
 
 
@@ -225,7 +235,7 @@ def build_sweep_plan(vertices: torch.Tensor, conn32: torch.Tensor, row_ind: torc
     keep = [seg_visit_ptr.contiguous(), seg_chunk_ptr.to(torch.int32).contiguous(), visits, chunk_rec]
     stats = dict(n_segments=n_seg, n_chunks=n_chunks, n_visits=n_vis, n_strips=n_strips, sweep_axis=s_ax,
                  visits_per_element=n_vis / E, max_deg=max_deg,
-                 row_tiles_per_vertex=float(((3 * cnt + 7) // 8).sum().item()) / max(n_act, 1))
+                 row_tiles_per_vertex=float(((cnt + 1) // 2).sum().item()) / max(n_act, 1))   # two nodes per row tile
     struct = None
     if vertices.is_cuda:
         if int(_lib.load().feb200_fused_sweep_warps(max_deg)) < 1:

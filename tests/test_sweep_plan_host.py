@@ -134,7 +134,7 @@ def test_sweep_strips_are_columns_on_a_structured_grid():
     st = plan.stats
     assert st["sweep_axis"] == 2                                     # vertex ids run fastest along z
     # 2 x 2 columns: 9 elements per layer of 4 vertices in the interior -> ~2.25 visits per element, 3.75 row tiles per vertex
-    assert st["visits_per_element"] < 2.8 and st["row_tiles_per_vertex"] < 4.2, st
+    assert st["visits_per_element"] < 2.8 and st["row_tiles_per_vertex"] < 4.6, st
 
 
 def test_sweep_plan_rejects_ineligible_meshes():
