@@ -542,6 +542,8 @@ static int launch_tangent(Kern kern, cudaStream_t st, const feb200_batch& b, con
     return FEB200_OK;
 }
 
+int tangent_iso_mma(cudaStream_t st, const feb200_batch& b, const double* x_vd, double* K_e);   // tangent_mma.cu
+
 }  // namespace feb
 
 using namespace feb;
@@ -586,6 +588,14 @@ int feb200_element_tangent(feb200_stream s, const feb200_batch* bp, const double
     TangentCfg c;
     const bool cm = (b.layout != LAYOUT_EQM);
     constexpr int PASSES_HEX = 2;
+    if (iso && b.D == 3 && b.N > 10) {       // many-node elements (hex27): block products on the FP64 tensor cores
+        rc = tangent_iso_mma(st, b, x_vd, K_e);
+        if (rc == FEB200_OK) {
+            FEB_CHECK_LAUNCH("element_tangent");
+            return FEB200_OK;
+        }
+        if (rc != FEB200_ERR_UNSUPPORTED) return rc;
+    }
 #ifndef FEB_GENERAL_CT_MAX_NU
 #define FEB_GENERAL_CT_MAX_NU 30      /* general (state-dependent) tangent: longer block rows (hex27, quad9 ...) go to the runtime-N kernel; tet10 (30) spills but is 3x faster compiled */
 #endif
