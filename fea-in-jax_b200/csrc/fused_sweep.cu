@@ -93,7 +93,7 @@ static inline SwSmem sweep_layout(int max_deg) {
     size_t o = (size_t)(8 * SW_DPHI + 8) * 8 + 8 * 4;    // basis table + weights + slot starts (shared by the block)
     L.off_warps = (o + 15) & ~(size_t)15;
     int w = 0;
-    L.off_rk = w;    w += 2 * 4 * 64 * 2;                // [2][4 elements][8][8] uint16 slot ranks (double buffered)
+    L.off_rk = w;    w += 2 * 4 * 64;                    // [2][4 elements][8][8] uint8 slot ranks (double buffered)
     L.off_rec = w;   w += 3 * 4 * SW_REC * 4;            // [3][4] visit records (groups g, g+1, g+2)
     L.off_info = w;  w += 4 * 64;                        // [4] chunk records {v[4], deg[4], p0[4]}
     L.off_flg = w;   w += 3 * 4 * 32;                    // [3][4 vertices][32 ranks] Dirichlet flag bytes
@@ -131,69 +131,108 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // 4-double bank groups.
 __device__ __forceinline__ int sw_grow(int n, int d) { return 8 * d + (((n < 4 ? n : 11 - n) + 2 * d) & 7); }
 
-// Row tiles 0..NMT-1 of one visit.  Rows: the visit's in-window nodes in ascending local order, component-major
-// (row R: component R / cnt, node position R % cnt); columns: component-major (column tile nt = component, column in
-// tile = local node).
+// Row tiles 0..NMT-1 of one visit, in three stages so that two independent visits can be interleaved (sweep_pair).
+// Rows: the visit's in-window nodes in ascending local order, two per row tile (rows 0-2 / 4-6 = the three components of a
+// node: FEB_SW_ROWS6); columns: component-major (column tile nt = component, column in tile = local node).
 template <int NMT>
-__device__ __forceinline__ void sweep_rows(const double* __restrict__ Ge, const double (&Bf)[3][2], double w0, double w1,
-                                           const uint16_t* __restrict__ rk, unsigned slotw, unsigned perm, int cnt,
-                                           double* __restrict__ panel, const int* __restrict__ sbase, int gid, int tig, int node0, int node1) {
+struct SwRows {
     double A[NMT][2];
     double* base0[NMT];
     double* base1[NMT];
     bool valid[NMT];
     double C[NMT][3][2];
+
+    // addresses, weighted A fragments, accumulators loaded from the panels
+    __device__ __forceinline__ void load(const double* __restrict__ Ge, double w0, double w1, const uint8_t* __restrict__ rk,
+                                         unsigned slotw, unsigned perm, int cnt, double* __restrict__ panel,
+                                         const int* __restrict__ sbase, int gid, int tig, int node0, int node1) {
 #pragma unroll
-    for (int mt = 0; mt < NMT; ++mt) {
+        for (int mt = 0; mt < NMT; ++mt) {
 #if FEB_SW_ROWS6
-        const int s = 2 * mt + (gid >> 2), d = gid & 3;
-        valid[mt] = d < 3 && s < cnt;
+            const int s = 2 * mt + (gid >> 2), d = gid & 3;
+            valid[mt] = d < 3 && s < cnt;
 #elif FEB_SW_DMAJOR
-        const int R = 8 * mt + gid;
-        const int d = (R >= cnt ? 1 : 0) + (R >= 2 * cnt ? 1 : 0), s = R - d * cnt;
-        valid[mt] = R < 3 * cnt;
+            const int R = 8 * mt + gid;
+            const int d = (R >= cnt ? 1 : 0) + (R >= 2 * cnt ? 1 : 0), s = R - d * cnt;
+            valid[mt] = R < 3 * cnt;
 #else
-        const int R = 8 * mt + gid;
-        const int s = R / 3, d = R - 3 * s;
-        valid[mt] = s < cnt;
+            const int R = 8 * mt + gid;
+            const int s = R / 3, d = R - 3 * s;
+            valid[mt] = s < cnt;
 #endif
-        const int na = valid[mt] ? (int)((perm >> (4 * s)) & 7u) : 0;
-        const int dd = valid[mt] ? d : 0;
-        const int slot = (int)((slotw >> (4 * na)) & 7u);
-        double* pb = panel + sbase[slot] + dd * FEB_SW_DS;
-        base0[mt] = pb + (unsigned)rk[na * 8 + node0] * (unsigned)FEB_SW_BS;
-        base1[mt] = pb + (unsigned)rk[na * 8 + node1] * (unsigned)FEB_SW_BS;
-        const int gr = sw_grow(na, dd) * 4 + tig;
-        const double g0 = Ge[gr], g1 = Ge[SW_KS + gr];
-        A[mt][0] = valid[mt] ? w0 * g0 : 0.0;
-        A[mt][1] = valid[mt] ? w1 * g1 : 0.0;
+            const int na = valid[mt] ? (int)((perm >> (4 * s)) & 7u) : 0;
+            const int dd = valid[mt] ? d : 0;
+            const int slot = (int)((slotw >> (4 * na)) & 7u);
+            double* pb = panel + sbase[slot] + dd * FEB_SW_DS;
+            base0[mt] = pb + (unsigned)rk[na * 8 + node0] * (unsigned)FEB_SW_BS;
+            base1[mt] = pb + (unsigned)rk[na * 8 + node1] * (unsigned)FEB_SW_BS;
+            const int gr = sw_grow(na, dd) * 4 + tig;
+            const double g0 = Ge[gr], g1 = Ge[SW_KS + gr];
+            A[mt][0] = valid[mt] ? w0 * g0 : 0.0;
+            A[mt][1] = valid[mt] ? w1 * g1 : 0.0;
 #pragma unroll
-        for (int nt = 0; nt < 3; ++nt) {
-            C[mt][nt][0] = 0.0;
-            C[mt][nt][1] = 0.0;
-            if (valid[mt]) {
-                C[mt][nt][0] = base0[mt][nt * FEB_SW_KK];
-                C[mt][nt][1] = base1[mt][nt * FEB_SW_KK];
+            for (int nt = 0; nt < 3; ++nt) {
+                C[mt][nt][0] = 0.0;
+                C[mt][nt][1] = 0.0;
+                if (valid[mt]) {
+                    C[mt][nt][0] = base0[mt][nt * FEB_SW_KK];
+                    C[mt][nt][1] = base1[mt][nt * FEB_SW_KK];
+                }
             }
         }
     }
+    __device__ __forceinline__ void mma(const double (&Bf)[3][2], int ks) {
 #pragma unroll
-    for (int mt = 0; mt < NMT; ++mt)
+        for (int mt = 0; mt < NMT; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 3; ++nt) dmma884(C[mt][nt][0], C[mt][nt][1], A[mt][0], Bf[nt][0]);
+            for (int nt = 0; nt < 3; ++nt) dmma884(C[mt][nt][0], C[mt][nt][1], A[mt][ks], Bf[nt][ks]);
+    }
+    __device__ __forceinline__ void store() {
 #pragma unroll
-    for (int mt = 0; mt < NMT; ++mt)
+        for (int mt = 0; mt < NMT; ++mt)
+            if (valid[mt]) {
 #pragma unroll
-        for (int nt = 0; nt < 3; ++nt) dmma884(C[mt][nt][0], C[mt][nt][1], A[mt][1], Bf[nt][1]);
-#pragma unroll
-    for (int mt = 0; mt < NMT; ++mt)
-        if (valid[mt]) {
-#pragma unroll
-            for (int nt = 0; nt < 3; ++nt) {
-                base0[mt][nt * FEB_SW_KK] = C[mt][nt][0];
-                base1[mt][nt * FEB_SW_KK] = C[mt][nt][1];
+                for (int nt = 0; nt < 3; ++nt) {
+                    base0[mt][nt * FEB_SW_KK] = C[mt][nt][0];
+                    base1[mt][nt * FEB_SW_KK] = C[mt][nt][1];
+                }
             }
-        }
+    }
+};
+
+struct SwVisit {
+    const double* Ge;
+    const uint8_t* rk;
+    unsigned slotw, perm;
+    int cnt;
+    double Bf[3][2];
+    double w0, w1;
+};
+
+template <int NMT>
+__device__ __forceinline__ void sweep_rows(const SwVisit& v, double* __restrict__ panel, const int* __restrict__ sbase, int gid,
+                                           int tig, int node0, int node1) {
+    SwRows<NMT> r;
+    r.load(v.Ge, v.w0, v.w1, v.rk, v.slotw, v.perm, v.cnt, panel, sbase, gid, tig, node0, node1);
+    r.mma(v.Bf, 0);
+    r.mma(v.Bf, 1);
+    r.store();
+}
+
+// Two visits that touch disjoint panel slots (the plan pairs them): one instruction stream with two independent chains.
+template <int NA, int NB>
+__device__ __forceinline__ void sweep_pair(const SwVisit& va, const SwVisit& vb, double* __restrict__ panel,
+                                           const int* __restrict__ sbase, int gid, int tig, int node0, int node1) {
+    SwRows<NA> ra;
+    SwRows<NB> rb;
+    ra.load(va.Ge, va.w0, va.w1, va.rk, va.slotw, va.perm, va.cnt, panel, sbase, gid, tig, node0, node1);
+    rb.load(vb.Ge, vb.w0, vb.w1, vb.rk, vb.slotw, vb.perm, vb.cnt, panel, sbase, gid, tig, node0, node1);
+    ra.mma(va.Bf, 0);
+    rb.mma(vb.Bf, 0);
+    ra.mma(va.Bf, 1);
+    rb.mma(vb.Bf, 1);
+    ra.store();
+    rb.store();
 }
 
 // WM, how the material enters the quadrature weight (the Poisson ratio is one number for the batch):
@@ -203,7 +242,7 @@ __device__ __forceinline__ void sweep_rows(const double* __restrict__ Ge, const 
 template <bool ELIM, int WM>
 __global__ void __launch_bounds__(FEB_SW_MAXWARPS * 32, 1)
 k_fused_hex8_sweep(feb200_batch b, feb200_sweep_plan plan, SwSmem L, const double* __restrict__ x_vd,
-                   const uint16_t* __restrict__ slot_rank, const uint8_t* __restrict__ block_flags,
+                   const uint8_t* __restrict__ slot_rank, const uint8_t* __restrict__ block_flags,
                    double* __restrict__ values) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* s_dphi = reinterpret_cast<double*>(smem_raw);                    // [q] DPHI : [n][3]
@@ -212,7 +251,7 @@ k_fused_hex8_sweep(feb200_batch b, feb200_sweep_plan plan, SwSmem L, const doubl
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gid = lane >> 2, tig = lane & 3;
     unsigned char* mine = smem_raw + L.off_warps + (size_t)warp * L.per_warp;
-    uint16_t* rkbuf = reinterpret_cast<uint16_t*>(mine + L.off_rk);          // [2][4][64]
+    uint8_t* rkbuf = mine + L.off_rk;                                        // [2][4][64]
     int* recs = reinterpret_cast<int*>(mine + L.off_rec);                    // [3][4] REC
     int* info = reinterpret_cast<int*>(mine + L.off_info);                   // [4] 16 ints: v[4], deg[4], p0[4] (int64)
     uint8_t* flg = mine + L.off_flg;                                         // [3][4][32]
@@ -274,7 +313,7 @@ k_fused_hex8_sweep(feb200_batch b, feb200_sweep_plan plan, SwSmem L, const doubl
                 cp_async8(dst, src);
                 cp_async8(dst + 1, src + 1);
                 cp_async8(dst + 2, src + 2);
-                cp_async16(rkbuf + (gi & 1) * 256 + jj * 64 + qq * 8, slot_rank + (int64_t)el * 64 + qq * 8);
+                if (qq < 4) cp_async16(rkbuf + (gi & 1) * 256 + jj * 64 + qq * 16, slot_rank + (int64_t)el * 64 + qq * 16);
                 if (WM == 2) cp_async8(eqbuf + jj * 8 + qq, b.mp + ((int64_t)el * 8 + qq) * b.M);
                 if (WM == 1 && qq == 0) cp_async8(eqbuf + jj * 8, b.mp + (int64_t)el * b.M);
             }
@@ -339,28 +378,44 @@ k_fused_hex8_sweep(feb200_batch b, feb200_sweep_plan plan, SwSmem L, const doubl
             // ---- visits
 #pragma unroll 1
             for (int j = 0; j < 4; ++j) {
-                const int4 hd = *reinterpret_cast<const int4*>(rg + j * SW_REC);
+                int4 hd = *reinterpret_cast<const int4*>(rg + j * SW_REC);
                 if (hd.x < 0) break;
-                const unsigned slotw = (unsigned)hd.y, perm = (unsigned)hd.z;
-                const int cnt = hd.w & 0xf;
-                const double* Ge = Gw + j * SW_EL;
-                const uint16_t* rk = rkbuf + (gi & 1) * 256 + j * 64;
-                double Bf[3][2];
+                auto fetch = [&](SwVisit& v, const int4& h, int jv) {
+                    v.slotw = (unsigned)h.y;
+                    v.perm = (unsigned)h.z;
+                    v.cnt = h.w & 0xf;
+                    v.Ge = Gw + jv * SW_EL;
+                    v.rk = rkbuf + (gi & 1) * 256 + jv * 64;
 #pragma unroll
-                for (int nt = 0; nt < 3; ++nt) {
-                    Bf[nt][0] = Ge[sw_grow(bnode, nt) * 4 + tig];
-                    Bf[nt][1] = Ge[SW_KS + sw_grow(bnode, nt) * 4 + tig];
-                }
-                const double w0 = Ge[96 + tig], w1 = Ge[SW_KS + 96 + tig];
+                    for (int nt = 0; nt < 3; ++nt) {
+                        v.Bf[nt][0] = v.Ge[sw_grow(bnode, nt) * 4 + tig];
+                        v.Bf[nt][1] = v.Ge[SW_KS + sw_grow(bnode, nt) * 4 + tig];
+                    }
+                    v.w0 = v.Ge[96 + tig];
+                    v.w1 = v.Ge[SW_KS + 96 + tig];
+                };
+                SwVisit va;
+                fetch(va, hd, j);
 #if FEB_SW_ROWS6
-                if (cnt > 6) sweep_rows<4>(Ge, Bf, w0, w1, rk, slotw, perm, cnt, panel, s_sbase, gid, tig, node0, node1);
-                else if (cnt > 4) sweep_rows<3>(Ge, Bf, w0, w1, rk, slotw, perm, cnt, panel, s_sbase, gid, tig, node0, node1);
-                else if (cnt > 2) sweep_rows<2>(Ge, Bf, w0, w1, rk, slotw, perm, cnt, panel, s_sbase, gid, tig, node0, node1);
-                else sweep_rows<1>(Ge, Bf, w0, w1, rk, slotw, perm, cnt, panel, s_sbase, gid, tig, node0, node1);
+                if (hd.w & 0x100) {          // paired with the next visit (disjoint panel slots, both with <= 4 in-window nodes)
+                    const int4 hb = *reinterpret_cast<const int4*>(rg + (j + 1) * SW_REC);
+                    SwVisit vb;
+                    fetch(vb, hb, j + 1);
+                    const bool a2 = va.cnt > 2, b2 = vb.cnt > 2;
+                    if (a2 && b2) sweep_pair<2, 2>(va, vb, panel, s_sbase, gid, tig, node0, node1);
+                    else if (a2) sweep_pair<2, 1>(va, vb, panel, s_sbase, gid, tig, node0, node1);
+                    else if (b2) sweep_pair<1, 2>(va, vb, panel, s_sbase, gid, tig, node0, node1);
+                    else sweep_pair<1, 1>(va, vb, panel, s_sbase, gid, tig, node0, node1);
+                    hd = hb;                 // the chunks completed by the pair are recorded on its second visit
+                    ++j;
+                } else if (va.cnt > 6) sweep_rows<4>(va, panel, s_sbase, gid, tig, node0, node1);
+                else if (va.cnt > 4) sweep_rows<3>(va, panel, s_sbase, gid, tig, node0, node1);
+                else if (va.cnt > 2) sweep_rows<2>(va, panel, s_sbase, gid, tig, node0, node1);
+                else sweep_rows<1>(va, panel, s_sbase, gid, tig, node0, node1);
 #else
-                if (cnt > 5) sweep_rows<3>(Ge, Bf, w0, w1, rk, slotw, perm, cnt, panel, s_sbase, gid, tig, node0, node1);
-                else if (cnt > 2) sweep_rows<2>(Ge, Bf, w0, w1, rk, slotw, perm, cnt, panel, s_sbase, gid, tig, node0, node1);
-                else sweep_rows<1>(Ge, Bf, w0, w1, rk, slotw, perm, cnt, panel, s_sbase, gid, tig, node0, node1);
+                if (va.cnt > 5) sweep_rows<3>(va, panel, s_sbase, gid, tig, node0, node1);
+                else if (va.cnt > 2) sweep_rows<2>(va, panel, s_sbase, gid, tig, node0, node1);
+                else sweep_rows<1>(va, panel, s_sbase, gid, tig, node0, node1);
 #endif
                 __syncwarp();
                 // ---- chunks completed by this visit: combine, eliminate, store, clear
@@ -462,8 +517,9 @@ int feb200_sweep_block_flags(feb200_stream s, int64_t V, const int64_t* nindptr,
 }
 
 int feb200_assemble_fused_hex8_sweep(feb200_stream s, const feb200_batch* bp, const feb200_sweep_plan* plan, const double* x_vd,
-                                     const uint16_t* slot_rank, const uint8_t* block_flags, int32_t material_hints,
+                                     const uint8_t* slot_rank8, const uint8_t* block_flags, int32_t material_hints,
                                      double* values) {
+    const uint8_t* slot_rank = slot_rank8;
     FEB_REQUIRE(bp && plan && x_vd && slot_rank && values, FEB200_ERR_INVALID, "assemble_fused_hex8_sweep: null pointer");
     const feb200_batch& b = *bp;
     FEB_REQUIRE(b.N == 8 && b.Q == 8 && b.D == 3, FEB200_ERR_UNSUPPORTED,

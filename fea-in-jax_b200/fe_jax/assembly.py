@@ -297,6 +297,8 @@ class _Plan:
                 from .sweep_plan import build_sweep_plan
                 row, col = self._keep[i]
                 plan = build_sweep_plan(ebc._vertices, ebc._conn32[i], row, col, self.pattern.nindptr)
+            if plan is not None:
+                plan.rank8 = self.slot_rank[i].to(torch.uint8).contiguous()      # ranks < 32: one byte per node pair for the kernel
             self._sweep[i] = plan
         return self._sweep[i]
 
@@ -399,8 +401,9 @@ def _assemble_values(element_residual_func, ebc, assembly_map_b, u, mask=None, v
         if (b.kind == _lib.KIND_LINEAR and b.material == _lib.MAT_ISOTROPIC and _use_sweep_kernel(ebc, i, b)
                 and plan.sweep_plan(ebc, i) is not None):
             flags = _block_flags(ebc, pat, mask) if (eliminate and mask is not None) else None
-            _lib.call("feb200_assemble_fused_hex8_sweep", b, plan.sweep_plan(ebc, i).struct, _lib.ptr(ebc._vertices),
-                      _lib.ptr(plan.slot_rank[i]), _lib.ptr(flags), _material_hints(ebc, i, b), _lib.ptr(vals))
+            sp = plan.sweep_plan(ebc, i)
+            _lib.call("feb200_assemble_fused_hex8_sweep", b, sp.struct, _lib.ptr(ebc._vertices), _lib.ptr(sp.rank8),
+                      _lib.ptr(flags), _material_hints(ebc, i, b), _lib.ptr(vals))
             continue
         if (b.kind == _lib.KIND_LINEAR and b.material == _lib.MAT_ISOTROPIC and plan.fused_plan(ebc, i) is not None):
             fp = plan.fused_plan(ebc, i)

@@ -212,6 +212,29 @@ def build_sweep_plan(vertices: torch.Tensor, conn32: torch.Tensor, row_ind: torc
     mask.scatter_add_(0, vinv, torch.ones_like(n_a) << n_a)
     lut_perm, lut_cnt = _perm_lut(dev)
     perm, cnt = lut_perm[mask], lut_cnt[mask]
+    # ---- order within a step: visits that touch disjoint panel slots next to each other, so that the kernel can run them
+    #      as one interleaved instruction stream (two independent DMMA / accumulator chains).  A pair occupies positions
+    #      (2m, 2m+1) of its segment (groups of four never split a pair); visits with more than four in-window nodes run alone
+    #      and go to the front of steps that start at an odd position, to the back otherwise.
+    smask = torch.zeros(n_vis, dtype=torch.int64, device=dev)
+    smask.scatter_add_(0, vinv, torch.ones_like(e_slot) << e_slot)
+    seg_first = torch.searchsorted(v_seg.contiguous(), torch.arange(n_seg, device=dev))
+    pos = torch.arange(n_vis, device=dev) - seg_first[v_seg]
+    new_step = torch.ones(n_vis, dtype=torch.bool, device=dev)
+    new_step[1:] = (v_seg[1:] != v_seg[:-1]) | (v_step[1:] != v_step[:-1])
+    gid = torch.cumsum(new_step.to(torch.int64), 0) - 1
+    start_odd = (pos[new_step] & 1)[gid]
+    popc = lut_cnt[smask]
+    alone = cnt > 4
+    cls = torch.where(alone, torch.where(start_odd == 1, torch.zeros_like(cnt), torch.full_like(cnt, 2)), torch.ones_like(cnt))
+    comp = torch.minimum(smask, 0xFF ^ smask)
+    okey = (gid << 24) | (cls << 20) | (popc << 16) | (comp << 8) | smask
+    order_v = torch.argsort(okey, stable=True)
+    v_elem, v_seg, v_step, slotw, perm, cnt, smask = (t[order_v] for t in (v_elem, v_seg, v_step, slotw, perm, cnt, smask))
+    pair_first = torch.zeros(n_vis, dtype=torch.bool, device=dev)
+    if n_vis > 1:
+        pair_first[:-1] = ((pos[:-1] & 1) == 0) & (v_seg[1:] == v_seg[:-1]) & (v_step[1:] == v_step[:-1]) & \
+                          ((smask[1:] & smask[:-1]) == 0) & (cnt[1:] <= 4) & (cnt[:-1] <= 4)
     # chunks completed by a visit: the last visit of step c retires chunks c .. (next step with visits) - 1
     last = torch.ones(n_vis, dtype=torch.bool, device=dev)
     last[:-1] = (v_seg[1:] != v_seg[:-1]) | (v_step[1:] != v_step[:-1])
@@ -223,7 +246,7 @@ def build_sweep_plan(vertices: torch.Tensor, conn32: torch.Tensor, row_ind: torc
     first_of_seg[1:] = v_seg[1:] != v_seg[:-1]
     if int(nret.max().item()) > 15 or bool((v_step[first_of_seg] != 0).any().item()):
         return None
-    flags = cnt | (nret << 4)
+    flags = cnt | (nret << 4) | (pair_first.to(torch.int64) << 8)
     head = torch.stack([v_elem, slotw, perm, flags], dim=1)
     head = torch.where(head >= (1 << 31), head - (1 << 32), head).to(torch.int32)
     visits = torch.cat([head, conn32[v_elem].to(torch.int32)], dim=1).contiguous()
@@ -234,7 +257,7 @@ def build_sweep_plan(vertices: torch.Tensor, conn32: torch.Tensor, row_ind: torc
                            chunk_p0.reshape(-1, 4).contiguous().view(torch.int32).reshape(-1, 8)], dim=1).contiguous()
     keep = [seg_visit_ptr.contiguous(), seg_chunk_ptr.to(torch.int32).contiguous(), visits, chunk_rec]
     stats = dict(n_segments=n_seg, n_chunks=n_chunks, n_visits=n_vis, n_strips=n_strips, sweep_axis=s_ax,
-                 visits_per_element=n_vis / E, max_deg=max_deg,
+                 visits_per_element=n_vis / E, max_deg=max_deg, paired_fraction=2.0 * float(pair_first.sum().item()) / n_vis,
                  row_tiles_per_vertex=float(((cnt + 1) // 2).sum().item()) / max(n_act, 1))   # two nodes per row tile
     struct = None
     if vertices.is_cuda:

@@ -199,7 +199,9 @@ int feb200_assemble_fused_hex8_mma(feb200_stream s, const feb200_batch* b, const
  * 8 panel slots of the warp, chunk c in slots 4*(c&1)..) and a list of visits sorted by step.  A visit is one 48-byte
  * record of 12 int32 {element, slotw, perm, flags, conn[8]}: slotw nibble n = panel slot of local node n (0xF: the node is
  * not in the window), perm nibble i = i-th in-window node (ascending), flags = count of in-window nodes | (chunks
- * completed by this visit) << 4, conn = the element's vertex ids.  A chunk record is 64 bytes: int32 v[4] (vertex id,
+ * completed by this visit) << 4 | (runs interleaved with the next visit: disjoint panel slots, positions 2m / 2m+1 of the
+ * segment, both with <= 4 in-window nodes) << 8, conn = the element's vertex ids.  slot_rank8 = the slot-rank map of
+ * feb200_slot_rank narrowed to one byte per node pair (degree <= 32).  A chunk record is 64 bytes: int32 v[4] (vertex id,
  * -1: empty slot), int32 deg[4] (its degree), int64 p0[4] (nindptr[vertex]).
  * Built by fe_jax/sweep_plan.py for any hex8 connectivity with vertex valence <= 8 and degree <= 32.  Needs one Poisson
  * ratio for the batch: layout (M,) or FEB200_HINT_UNIFORM_POISSON.  block_flags != NULL fuses apply_dirichlet_bcs_lhs:
@@ -220,7 +222,7 @@ int32_t feb200_fused_sweep_warps(int32_t max_deg);   /* workers (warps) per SM t
 int feb200_sweep_block_flags(feb200_stream s, int64_t V, const int64_t* nindptr, const int32_t* nindices,
                              const uint8_t* vertex_flags, uint8_t* block_flags);
 int feb200_assemble_fused_hex8_sweep(feb200_stream s, const feb200_batch* b, const feb200_sweep_plan* plan, const double* x_vd,
-                                     const uint16_t* slot_rank, const uint8_t* block_flags, int32_t material_hints,
+                                     const uint8_t* slot_rank8, const uint8_t* block_flags, int32_t material_hints,
                                      double* values);
 
 /* apply_dirichlet_bcs_lhs on the node-pattern CSR (sparse_matrix.py:157-184). mask: (U*V) 0/1 doubles. */

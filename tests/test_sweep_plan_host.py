@@ -87,6 +87,12 @@ def test_sweep_plan_data_flow_reproduces_oracle_jacobian(dims, shuffle, seg_chun
         for vi in range(seg_vptr[seg], seg_vptr[seg + 1]):
             e, slotw, perm, flags = (int(x) & 0xFFFFFFFF for x in visits[vi, :4])
             cnt, nret = flags & 0xF, (flags >> 4) & 0xF
+            if flags & 0x100:                                        # first of a pair the kernel runs as one instruction stream:
+                e2, slotw2, _, flags2 = (int(x) & 0xFFFFFFFF for x in visits[vi + 1, :4])
+                s1 = {(slotw >> (4 * n)) & 0xF for n in range(8)} - {0xF}
+                s2 = {(slotw2 >> (4 * n)) & 0xF for n in range(8)} - {0xF}
+                assert (vi - seg_vptr[seg]) % 2 == 0 and vi + 1 < seg_vptr[seg + 1]      # positions (2m, 2m+1) of the segment
+                assert not (s1 & s2) and nret == 0 and cnt <= 4 and (flags2 & 0xF) <= 4 and not (flags2 & 0x100)
             Gm = g[e].transpose(1, 2, 0).reshape(24, 8)              # rows (n, d), columns q
             S = (Gm * (detJ[e] * Wr * mu_q[e])) @ Gm.T               # the material enters through the weights
             in_window = [n for n in range(8) if (slotw >> (4 * n)) & 0xF != 0xF]
