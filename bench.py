@@ -406,7 +406,7 @@ def main():
         bflags = _block_flags(ebc, pat, mask)
         kernels["assemble_fused_hex8"] = lambda: _lib.call(
             "feb200_assemble_fused_hex8_sweep", bstruct, sweep.struct, _lib.ptr(ebc._vertices), _lib.ptr(sweep.rank8),
-            _lib.ptr(bflags), _material_hints(ebc, 0, bstruct), _lib.ptr(J_vals))
+            _lib.ptr(bflags), _material_hints(ebc, 0, bstruct), _lib.ptr(J_vals), 0)
     elif use_mma:
         kernels["assemble_fused_hex8"] = lambda: _lib.call(
             "feb200_assemble_fused_hex8_mma", bstruct, fused.struct, _lib.ptr(ebc._vertices), _lib.ptr(plan.slot_rank[0]),

@@ -239,7 +239,7 @@ __device__ __forceinline__ void sweep_pair(const SwVisit& va, const SwVisit& vb,
 //   0  not at all: one (lambda, mu) for the batch, applied when a chunk is stored               layout (M,)
 //   1  w_q * mu_e                                                                               layout (E,M)
 //   2  w_q * E_q / (2 (1 + nu))                                                                 layout (E,Q,M)
-template <bool ELIM, int WM>
+template <bool ELIM, int WM, bool ACC>
 __global__ void __launch_bounds__(FEB_SW_MAXWARPS * 32, 1)
 k_fused_hex8_sweep(feb200_batch b, feb200_sweep_plan plan, SwSmem L, const double* __restrict__ x_vd,
                    const uint8_t* __restrict__ slot_rank, const uint8_t* __restrict__ block_flags,
@@ -445,7 +445,15 @@ k_fused_hex8_sweep(feb200_batch b, feb200_sweep_plan plan, SwSmem L, const doubl
 #pragma unroll
                                 for (int kk = 0; kk < 3; ++kk)
                                     K[d * 3 + kk] = u_lam * S[d * 3 + kk] + u_mu * S[kk * 3 + d] + (d == kk ? tr : 0.0);
-                            if (ELIM) {
+                            double* dst = values + 9 * p0 + 3 * lane;
+                            const int row_len = 3 * deg;
+                            if (ACC) {           // a later batch of a multi-batch mesh: add to what the earlier batches stored
+#pragma unroll
+                                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                                    for (int jx = 0; jx < 3; ++jx) K[i * 3 + jx] += __ldcs(dst + (int64_t)i * row_len + jx);
+                            }
+                            if (ELIM) {          // (on the sum over all batches when accumulating: pass the flags with the last batch)
                                 const unsigned f = flg[((cr % 3) * 4 + s) * 32 + lane];
                                 const unsigned cf = f & 7u, diag = f & 8u, rf = (f >> 4) & 7u;
                                 if (cf | rf) {
@@ -457,8 +465,6 @@ k_fused_hex8_sweep(feb200_batch b, feb200_sweep_plan plan, SwSmem L, const doubl
                                                 K[i * 3 + jx] = (((rf >> i) & 1u) && diag && i == jx) ? 1.0 : 0.0;
                                 }
                             }
-                            double* dst = values + 9 * p0 + 3 * lane;
-                            const int row_len = 3 * deg;
 #pragma unroll
                             for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -518,7 +524,7 @@ int feb200_sweep_block_flags(feb200_stream s, int64_t V, const int64_t* nindptr,
 
 int feb200_assemble_fused_hex8_sweep(feb200_stream s, const feb200_batch* bp, const feb200_sweep_plan* plan, const double* x_vd,
                                      const uint8_t* slot_rank8, const uint8_t* block_flags, int32_t material_hints,
-                                     double* values) {
+                                     double* values, int32_t accumulate) {
     const uint8_t* slot_rank = slot_rank8;
     FEB_REQUIRE(bp && plan && x_vd && slot_rank && values, FEB200_ERR_INVALID, "assemble_fused_hex8_sweep: null pointer");
     const feb200_batch& b = *bp;
@@ -542,19 +548,22 @@ int feb200_assemble_fused_hex8_sweep(feb200_stream s, const feb200_batch* bp, co
     const int64_t want = ceil_div(plan->n_segments, L.warps);
     const int grid = (int)(want < sm_count() ? want : sm_count());
     const int wm = (b.layout == FEB200_LAYOUT_EQM) ? 2 : (b.layout == FEB200_LAYOUT_EM ? 1 : 0);
-    static bool attr_set[2][3] = {{false, false, false}, {false, false, false}};
-#define FEB_SW_LAUNCH(EL, WMODE)                                                                                       \
+    static bool attr_set[2][3][2] = {};
+#define FEB_SW_LAUNCH(EL, WMODE, AC)                                                                                   \
     {                                                                                                                  \
-        auto kern = k_fused_hex8_sweep<EL, WMODE>;                                                                     \
-        if (!attr_set[EL ? 1 : 0][WMODE]) {                                                                            \
+        auto kern = k_fused_hex8_sweep<EL, WMODE, AC>;                                                                 \
+        if (!attr_set[EL ? 1 : 0][WMODE][AC ? 1 : 0]) {                                                                \
             FEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM_MAX));       \
-            attr_set[EL ? 1 : 0][WMODE] = true;                                                                        \
+            attr_set[EL ? 1 : 0][WMODE][AC ? 1 : 0] = true;                                                            \
         }                                                                                                              \
         kern<<<grid, L.warps * 32, L.total, st>>>(b, *plan, L, x_vd, slot_rank, block_flags, values);                  \
     }
+#define FEB_SW_DISPATCH2(EL, AC)                                                                                       \
+    if (wm == 0) FEB_SW_LAUNCH(EL, 0, AC) else if (wm == 1) FEB_SW_LAUNCH(EL, 1, AC) else FEB_SW_LAUNCH(EL, 2, AC)
 #define FEB_SW_DISPATCH(EL)                                                                                            \
-    if (wm == 0) FEB_SW_LAUNCH(EL, 0) else if (wm == 1) FEB_SW_LAUNCH(EL, 1) else FEB_SW_LAUNCH(EL, 2)
+    if (accumulate) { FEB_SW_DISPATCH2(EL, true) } else { FEB_SW_DISPATCH2(EL, false) }
     if (block_flags) { FEB_SW_DISPATCH(true) } else { FEB_SW_DISPATCH(false) }
+#undef FEB_SW_DISPATCH2
 #undef FEB_SW_DISPATCH
 #undef FEB_SW_LAUNCH
     FEB_CHECK_LAUNCH("assemble_fused_hex8_sweep");

@@ -97,7 +97,7 @@ SIGNATURES = {
     "feb200_assemble_fused_hex8_mma": (c_int32, [_P, POINTER(Batch), POINTER(FusedPlan), _P, _P, _P, _P, _I32, _P]),
     "feb200_fused_sweep_warps": (c_int32, [_I32]),
     "feb200_sweep_block_flags": (c_int32, [_P, _I64, _P, _P, _P, _P]),
-    "feb200_assemble_fused_hex8_sweep": (c_int32, [_P, POINTER(Batch), POINTER(SweepPlan), _P, _P, _P, _I32, _P]),
+    "feb200_assemble_fused_hex8_sweep": (c_int32, [_P, POINTER(Batch), POINTER(SweepPlan), _P, _P, _P, _I32, _P, _I32]),
     "feb200_dirichlet_lhs": (c_int32, [_P, _I64, _I32, _P, _P, _P, _P]),
     "feb200_dirichlet_lhs_coo": (c_int32, [_P, _I64, _P, _P, _P, _P, _P]),
     "feb200_csr_diagonal": (c_int32, [_P, _I64, _I32, _P, _P, _P, _P]),

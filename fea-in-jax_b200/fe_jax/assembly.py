@@ -292,7 +292,7 @@ class _Plan:
         """Streaming plan of feb200_assemble_fused_hex8_sweep for batch i (None when the mesh is not eligible)."""
         if i not in self._sweep:
             plan = None
-            if (os.environ.get("FEB200_FUSED", "1") != "0" and ebc.B == 1 and ebc.N[i] == 8 and ebc.Q[i] == 8
+            if (os.environ.get("FEB200_FUSED", "1") != "0" and ebc.N[i] == 8 and ebc.Q[i] == 8
                     and ebc.D == 3 and self.pattern.max_deg <= 32):
                 from .sweep_plan import build_sweep_plan
                 row, col = self._keep[i]
@@ -394,18 +394,25 @@ def _assemble_values(element_residual_func, ebc, assembly_map_b, u, mask=None, v
     plan = _plan(ebc, assembly_map_b)
     pat = plan.pattern
     vals = out if out is not None else torch.empty(pat.nnz, dtype=torch.float64, device=u.device)
+    # Several batches (fea.py:885-889 sums them): the values start from zero, every batch accumulates -- the streaming
+    # fused kernel for its hex8 batches, the two-pass path for the rest -- and the Dirichlet elimination runs once on the
+    # finished sums.  One batch: the kernels overwrite and fuse the elimination into their store.
+    multi = ebc.B > 1
+    if multi:
+        vals.zero_()
     for i in range(ebc.B):
         b = ebc._batch_struct(i, res.kind)
-        # fused paths: linear isotropic hex8 (any material layout), single batch (tangent independent of u).
-        # Streaming kernel when the batch has one Poisson ratio, else the tile kernels.
+        # fused paths: linear isotropic hex8 (any material layout; the tangent does not depend on u).
+        # Streaming kernel when the batch has one Poisson ratio, else (single batch) the tile kernels.
         if (b.kind == _lib.KIND_LINEAR and b.material == _lib.MAT_ISOTROPIC and _use_sweep_kernel(ebc, i, b)
                 and plan.sweep_plan(ebc, i) is not None):
-            flags = _block_flags(ebc, pat, mask) if (eliminate and mask is not None) else None
+            flags = _block_flags(ebc, pat, mask) if (eliminate and mask is not None and not multi) else None
             sp = plan.sweep_plan(ebc, i)
             _lib.call("feb200_assemble_fused_hex8_sweep", b, sp.struct, _lib.ptr(ebc._vertices), _lib.ptr(sp.rank8),
-                      _lib.ptr(flags), _material_hints(ebc, i, b), _lib.ptr(vals))
+                      _lib.ptr(flags), _material_hints(ebc, i, b), _lib.ptr(vals), 1 if multi else 0)
             continue
-        if (b.kind == _lib.KIND_LINEAR and b.material == _lib.MAT_ISOTROPIC and plan.fused_plan(ebc, i) is not None):
+        if (not multi and b.kind == _lib.KIND_LINEAR and b.material == _lib.MAT_ISOTROPIC
+                and plan.fused_plan(ebc, i) is not None):
             fp = plan.fused_plan(ebc, i)
             flags = _vertex_flags(ebc, mask) if (eliminate and mask is not None) else None
             if _use_tensor_core_kernel(ebc, i, b, fp):
@@ -421,10 +428,12 @@ def _assemble_values(element_residual_func, ebc, assembly_map_b, u, mask=None, v
         _lib.call("feb200_element_tangent", b, _lib.ptr(ebc._vertices), _lib.ptr(u), _lib.ptr(mask), _lib.ptr(values),
                   _lib.ptr(K_e))
         bm = plan.maps[i]
-        elim = eliminate and mask is not None and i == ebc.B - 1
+        elim = eliminate and mask is not None and not multi
         _lib.call("feb200_assemble_csr", bm, pat.V, pat.U, _lib.ptr(K_e), _lib.ptr(plan.slot_rank[i]),
-                  _lib.ptr(pat.nindptr), pat.max_deg, _lib.ptr(vals), 1 if i > 0 else 0,
+                  _lib.ptr(pat.nindptr), pat.max_deg, _lib.ptr(vals), 1 if multi else 0,
                   _lib.ptr(pat.nindices) if elim else None, _lib.ptr(mask) if elim else None)
+    if multi and eliminate and mask is not None:
+        _lib.call("feb200_dirichlet_lhs", pat.V, pat.U, _lib.ptr(pat.nindptr), _lib.ptr(pat.nindices), _lib.ptr(mask), _lib.ptr(vals))
     return vals, pat
 
 
@@ -457,7 +466,7 @@ def _use_sweep_kernel(ebc, i, b) -> bool:
     the tile kernels instead."""
     if os.environ.get("FEB200_FUSED_IMPL", "sweep") != "sweep":
         return False
-    if os.environ.get("FEB200_FUSED", "1") == "0" or ebc.B != 1:
+    if os.environ.get("FEB200_FUSED", "1") == "0" or not (ebc.N[i] == 8 and ebc.Q[i] == 8 and ebc.D == 3):
         return False
     return b.layout == _lib.LAYOUT_M or _poisson_facts(ebc, i)[1]
 

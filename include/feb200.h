@@ -205,7 +205,9 @@ int feb200_assemble_fused_hex8_mma(feb200_stream s, const feb200_batch* b, const
  * -1: empty slot), int32 deg[4] (its degree), int64 p0[4] (nindptr[vertex]).
  * Built by fe_jax/sweep_plan.py for any hex8 connectivity with vertex valence <= 8 and degree <= 32.  Needs one Poisson
  * ratio for the batch: layout (M,) or FEB200_HINT_UNIFORM_POISSON.  block_flags != NULL fuses apply_dirichlet_bcs_lhs:
- * 32 bytes per vertex from feb200_sweep_block_flags (byte r = flags of CSR block r of the vertex row).  Replaces
+ * 32 bytes per vertex from feb200_sweep_block_flags (byte r = flags of CSR block r of the vertex row).  accumulate != 0 adds
+ * to `values` (later batches of a multi-batch mesh, fea.py:885-889; rows of vertices the batch does not touch stay as they
+ * are; pass block_flags with the LAST batch only: the elimination acts on the finished sums).  Replaces
  * fea.py:519-572 + :613-660 + sparse_matrix.py:157-184 like the kernels above. */
 typedef struct {
     int32_t n_segments;
@@ -223,7 +225,7 @@ int feb200_sweep_block_flags(feb200_stream s, int64_t V, const int64_t* nindptr,
                              const uint8_t* vertex_flags, uint8_t* block_flags);
 int feb200_assemble_fused_hex8_sweep(feb200_stream s, const feb200_batch* b, const feb200_sweep_plan* plan, const double* x_vd,
                                      const uint8_t* slot_rank8, const uint8_t* block_flags, int32_t material_hints,
-                                     double* values);
+                                     double* values, int32_t accumulate);
 
 /* apply_dirichlet_bcs_lhs on the node-pattern CSR (sparse_matrix.py:157-184). mask: (U*V) 0/1 doubles. */
 int feb200_dirichlet_lhs(feb200_stream s, int64_t V, int32_t U, const int64_t* nindptr, const int32_t* nindices,

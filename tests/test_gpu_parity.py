@@ -667,6 +667,38 @@ def test_fused_sweep_kernel_matches_tile_kernel_and_oracle(fj, layout, keep, dim
     assert torch.equal(out["sweep"][0], _assemble_values(token, ebc, maps, u)[0])
 
 
+def test_fused_sweep_kernel_on_a_multi_batch_mesh(fj):
+    """Two hex8 batches (different moduli, one Poisson ratio each) plus a tet4 batch on one vertex set: the hex8 batches go
+    through the streaming fused kernel in accumulate mode, the tet4 batch through the two-pass path, the Dirichlet
+    elimination runs once on the sums -- against the oracle's sum over batches (fea.py:885-889, :613-660)."""
+    from fe_jax.assembly import _assemble_values
+    from fe_jax import _lib
+    n = 6
+    Vx, cells = orc.uniform_hex_grid(n, n + 1, n + 2)
+    rng = np.random.default_rng(23)
+    Vx = Vx + 0.1 / n * rng.uniform(-1, 1, size=Vx.shape)
+    cells = cells[rng.permutation(cells.shape[0])]
+    half = cells.shape[0] // 2
+    tets = np.concatenate([cells[:40, [0, 1, 2, 4]], cells[:40, [7, 6, 5, 3]]])     # extra simplices on existing vertices
+    spec = [dict(cell="hexahedron", degree=1, qdeg=2, cells=cells[:half], model="elastic_isotropic", mp=np.array([70e9, 0.25])),
+            dict(cell="hexahedron", degree=1, qdeg=2, cells=cells[half:], model="elastic_isotropic",
+                 mp=np.stack([10e9 + 90e9 * rng.uniform(size=cells.shape[0] - half), np.full(cells.shape[0] - half, 0.3)], axis=1)),
+            dict(cell="tetrahedron", degree=1, qdeg=2, cells=tets, model="elastic_isotropic", mp=np.array([30e9, 0.2]))]
+    ebc, maps, token, prob, _ = build_pair(fj, Vx, spec)
+    u = torch.zeros(Vx.size, dtype=torch.float64, device="cuda")
+    dofs = np.unique(rng.integers(0, Vx.size, size=Vx.size // 9))
+    mask = torch.zeros(prob.F, dtype=torch.float64, device="cuda")
+    mask[torch.tensor(dofs, device="cuda")] = 1.0
+    before = dict(_lib.launches_by_name)
+    v0 = _assemble_values(token, ebc, maps, u)[0].clone()
+    v1 = _assemble_values(token, ebc, maps, u, mask, torch.zeros_like(mask), eliminate=True)[0].clone()
+    assert _lib.launches_by_name.get("feb200_assemble_fused_hex8_sweep", 0) - before.get("feb200_assemble_fused_hex8_sweep", 0) == 4
+    d_o, r_o, c_o = prob.jacobian_wo_dirichlet(np.zeros(Vx.size))
+    assert rel_err(v0, d_o) <= ASM_RTOL
+    assert rel_err(v1, orc.apply_dirichlet_bcs_lhs(d_o, r_o, c_o, dofs)) <= ASM_RTOL
+    assert torch.equal(v0, _assemble_values(token, ebc, maps, u)[0])
+
+
 def _lib_launches(fj):
     from fe_jax import _lib
     return dict(_lib.launches_by_name)
