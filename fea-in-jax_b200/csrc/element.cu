@@ -7,6 +7,8 @@
 //             K[(a,d),(b,k)] = sum_q detJ W sum_{i,l} g[a,i] dS[i,d]/dH[k,l] g[b,l]).
 // Coordinates and the solution are gathered from vertex arrays through `conn`; the Dirichlet
 // blend u_w = (1-m) u + m g (fea.py:948-950) is applied while gathering when a mask is given.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "element_math.cuh"
 
@@ -543,6 +545,8 @@ static int launch_tangent(Kern kern, cudaStream_t st, const feb200_batch& b, con
 }
 
 int tangent_iso_mma(cudaStream_t st, const feb200_batch& b, const double* x_vd, double* K_e);   // tangent_mma.cu
+int tangent_general_mma(cudaStream_t st, const feb200_batch& b, const double* x_vd, const double* u, const double* mask,
+                        const double* values, double* K_e);                                       // tangent_general_mma.cu
 
 }  // namespace feb
 
@@ -595,6 +599,17 @@ int feb200_element_tangent(feb200_stream s, const feb200_batch* bp, const double
             return FEB200_OK;
         }
         if (rc != FEB200_ERR_UNSUPPORTED) return rc;
+    }
+    if (!iso && b.D == 3 && b.N == 8 && b.Q == 8) {      // hex8, state-dependent law: nine 8 x 8 x 24 tensor-core products
+        static const bool scalar_only = getenv("FEB200_TANGENT_SCALAR") != nullptr;     // A/B switch for the profile drivers
+        if (!scalar_only) {
+            rc = tangent_general_mma(st, b, x_vd, u, mask, values, K_e);
+            if (rc == FEB200_OK) {
+                FEB_CHECK_LAUNCH("element_tangent");
+                return FEB200_OK;
+            }
+            if (rc != FEB200_ERR_UNSUPPORTED) return rc;
+        }
     }
 #ifndef FEB_GENERAL_CT_MAX_NU
 #define FEB_GENERAL_CT_MAX_NU 30      /* general (state-dependent) tangent: longer block rows (hex27, quad9 ...) go to the runtime-N kernel; tet10 (30) spills but is 3x faster compiled */
