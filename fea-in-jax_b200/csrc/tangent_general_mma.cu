@@ -12,12 +12,16 @@
 //   phase 1  lane = (element, quadrature point): coordinates / solution from the vertex arrays (Dirichlet blend fused),
 //            J, J^-1, the 24 physical gradients, H, then w A_q (closed form for St. Venant-Kirchhoff, forward-mode duals
 //            on the constitutive law otherwise) into shared memory;
-//   phase 2  per element, as nine 8 x 8 products over the 24 (point, i) pairs on mma.sync.m8n8k4.f64:
-//              K^{dk}[a][b] = sum_{(q,i)} g_q[a,i] * Y^{dk}[(q,i)][b],     Y^{dk}[(q,i)][b] = sum_l w A_q[(i,d),(k,l)] g_q[b,l]
-//            the lane that owns B-fragment entry ((q,i), b) forms Y in registers (3 multiply-adds per entry, A_q rows
-//            read as shared-memory broadcasts) and feeds it straight to the tensor core; the A fragment is one of the three
-//            gradient values it already holds.  A lane ends up with the two complete 3 x 3 blocks K[a][2t], K[a][2t+1] =
-//            144 contiguous bytes of K_e[(e*8 + a)][b][3][3];
+//   phase 2  per element, two chained tensor-core products (mma.sync.m8n8k4.f64), nothing scalar in between:
+//              product 1, per point:  Y_q[b][(i,d,k)] = sum_l g_q[b,l] * w A_q[(i,d),(k,l)]          (8 x 27 x 3: 5 DMMAs)
+//              product 2, per (d,k):  K^{dk}[a][b]    = sum_{(q,i)} g_q[a,i] * Y_q[b][(i,d,k)]       (8 x 8 x 24: 6 DMMAs)
+//            The accumulator fragment of product 1 IS the B fragment of product 2: the columns of product 1 are ordered so
+//            that the lane holding Y_q[b][(i,d,k)] is the lane that owns contraction slot (q,i) / column b of product 2
+//            (ownership of i rotates with the point through the four lanes of a quad; one register select per entry).
+//            Operands reach the lanes as fragments (no replicated reads): 54 shared-memory loads per element instead of the
+//            180 of the first version, whose scalar Y stage was bound by shared-memory wavefronts (profiles/
+//            r02_tangent_general_mma_v1_ncu_summary.txt).  A lane ends up with the two complete 3 x 3 blocks K[a][2t],
+//            K[a][2t+1] = 144 contiguous bytes of K_e[(e*8 + a)][b][3][3];
 //   store    the element's 4608 bytes are staged in the shared memory its A_q occupied and leave as ONE bulk asynchronous
 //            copy (cp.async.bulk shared -> global), overlapping the next element's products.
 #include "common.cuh"
@@ -25,7 +29,15 @@
 #include "hex8_mma.cuh"
 
 #ifndef FEB_TG_WARPS
-#define FEB_TG_WARPS 8
+#define FEB_TG_WARPS 12
+#endif
+#ifndef FEB_TG_GROUP
+#define FEB_TG_GROUP 4                    /* elements per group (lanes 8 * GROUP .. 31 idle in phase 1 when < 4) */
+#endif
+#ifndef FEB_TG_AGROUP
+#define FEB_TG_AGROUP 2                   /* elements of a group whose point tangents w A_q sit in shared memory at a time: the
+                                             lanes of the other elements keep H and w in registers and fill the same area
+                                             when their turn comes (20.7 KB of A per warp would cap the SM at 8 warps) */
 #endif
 
 namespace feb {
@@ -37,22 +49,39 @@ constexpr int TG_AQ = 81;                 // w A_q: [(i,d)][(k,l)]
 constexpr int TG_AE = 8 * TG_AQ;          // per element: 5184 bytes, reused as the 4608-byte staging of K_e
 constexpr int TG_DPHI = 26;               // doubles per point of the basis table (24 used; 16-byte rows, conflict-free)
 constexpr size_t TG_TABLE = (size_t)(8 * TG_DPHI + 8) * 8;
-constexpr size_t TG_PER_WARP = (size_t)(4 * TG_GE + 4 * TG_AE) * 8;
+constexpr int TG_GRP = FEB_TG_GROUP;
+constexpr int TG_AGRP = FEB_TG_AGROUP;    // elements whose w A_q is resident at a time
+static_assert(TG_GRP % TG_AGRP == 0, "FEB_TG_AGROUP must divide FEB_TG_GROUP");
+constexpr size_t TG_PER_WARP = (size_t)(TG_GRP * TG_GE + TG_AGRP * TG_AE) * 8;
 
-__device__ __forceinline__ double tg_load_u(const double* __restrict__ u, const double* __restrict__ mask,
-                                            const double* __restrict__ values, int64_t f) {
-    const double v = u[f];
-    if (!mask) return v;
-    const double m = mask[f];
-    return (1.0 - m) * v + m * values[f];
-}
-
-// w A_q of any law through forward-mode duals on the constitutive function (element_math.cuh); kept out of line so that
-// its local arrays do not weigh on the register allocation of the kernel
+// w A_q of any law through forward-mode duals on the constitutive function (element_math.cuh), three directions at a time
+// (the derivatives with respect to H[k][0..2] per pass: 36 live dual components instead of the 90 of point_tangent, which
+// ptxas keeps in local memory); out of line so that its registers do not weigh on the kernel.
 __device__ __noinline__ void tg_generic_tangent(int material, const double* mp, const double (&H)[3][3], double w, double* ad) {
-    double A[81];
-    point_tangent<3>(material, mp, H, A);
-    for (int i = 0; i < 81; ++i) ad[i] = w * A[i];
+    if (material == MAT_ISOTROPIC || material == MAT_ORTHOTROPIC) {         // constant tangent: no duals needed
+        double A[81];
+        point_tangent<3>(material, mp, H, A);
+        for (int i = 0; i < 81; ++i) ad[i] = w * A[i];
+        return;
+    }
+#pragma unroll 1
+    for (int k = 0; k < 3; ++k) {
+        Dual<3> Hd[3][3], Sd[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int l = 0; l < 3; ++l) {
+                Hd[i][l] = dual_const<3>(H[i][l]);
+                if (i == k) Hd[i][l].d[l] = 1.0;
+            }
+        point_stress<3, Dual<3>>(material, mp, Hd, Sd);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+#pragma unroll
+                for (int l = 0; l < 3; ++l) ad[(i * 3 + d) * 9 + k * 3 + l] = w * Sd[i][d].d[l];
+    }
 }
 
 __global__ void __launch_bounds__(FEB_TG_WARPS * 32, 1)
@@ -64,39 +93,64 @@ k_tangent_general_mma(feb200_batch b, const double* __restrict__ x_vd, const dou
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gid = lane >> 2, tig = lane & 3;
     double* Gw = reinterpret_cast<double*>(tg_raw + TG_TABLE + (size_t)warp * TG_PER_WARP);   // [4] GE : [q] GQ : [n][3]
-    double* Aw = Gw + 4 * TG_GE;                                            // [4] AE : [q] AQ
+    double* Aw = Gw + TG_GRP * TG_GE;                                            // [4] AE : [q] AQ
     for (int i = tid; i < 8 * 24; i += blockDim.x) s_dphi[(i / 24) * TG_DPHI + (i % 24)] = b.dphi[i];
     if (tid < 8) s_w[tid] = b.W[tid];
     __syncthreads();                                                        // the only block-wide barrier
 
     const int jj = lane >> 3, qq = lane & 7;                                // phase 1: element of the group, quadrature point
-    // phase 2, k-step s: this lane's contraction index m = 4 s + tig = 3 q + i
-    int offG[6], offA[6], isel[6];
+    // phase 2, per-lane constants (tests/test_tangent_mma_host.py restates this index scheme on the CPU).
+    // Product 1 (Y = g A^T per point q = 4 h + r): rows = node b (gid), contraction = l (tig; 3 is padding), columns
+    // c = 8 nt + gid: column c lands in the accumulators of lane-in-quad tig_o = (c % 8) / 2, slot dk = 2 nt + c % 2, and
+    // carries gradient component i = (tig_o - r) mod 4 (3 = idle): every point hands each (d,k) product three of the four
+    // contraction slots of a quad, rotating with the point, so the 24 (q,i) pairs fill exactly 6 k-steps of product 2.
+    const int tig_o = gid >> 1, jcol = gid & 1;
+    const int lB = tig < 3 ? tig : 2;                                       // tig = 3 multiplies a zero A entry: any finite value
+    const int offA1 = gid * 3 + lB;
+    int cB[5], io27[4];
 #pragma unroll
-    for (int s = 0; s < 6; ++s) {
-        const int m = 4 * s + tig, q = m / 3, i = m - 3 * q;
-        offG[s] = q * TG_GQ + gid * 3;
-        offA[s] = q * TG_AQ + i * 27;
-        isel[s] = i;
+    for (int nt = 0; nt < 5; ++nt) {
+        const int dk = 2 * nt + jcol;
+        cB[nt] = (dk < 8 ? dk : 8) * 3 + lB;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = (tig_o - r) & 3;
+        io27[r] = 27 * (i < 3 ? i : 2);
+    }
+    // Product 2, step (h, st): this lane's slot holds point 4 h + rsel[st], component (tig - rsel[st]) mod 4
+    const bool sel0 = (tig == 3), sel1 = (tig == 0 || tig == 3), sel2 = (tig == 2);
+    int offAop[6];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int r0 = sel0 ? 1 : 0, r1 = sel1 ? 2 : 1, r2 = sel2 ? 2 : 3;
+        offAop[3 * h + 0] = (4 * h + r0) * TG_GQ + gid * 3 + ((tig - r0) & 3);
+        offAop[3 * h + 1] = (4 * h + r1) * TG_GQ + gid * 3 + ((tig - r1) & 3);
+        offAop[3 * h + 2] = (4 * h + r2) * TG_GQ + gid * 3 + ((tig - r2) & 3);
     }
     const bool hyper = (b.kind == KIND_HYPER);
-    const int64_t n_groups = (b.E + 3) >> 2;
+    const int64_t n_groups = (b.E + TG_GRP - 1) / TG_GRP;
     const int64_t n_workers = (int64_t)gridDim.x * (blockDim.x >> 5);
 
     for (int64_t grp = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; grp < n_groups; grp += n_workers) {
-        const int64_t e = 4 * grp + jj;
-        const bool act = e < b.E;
+        const int64_t e = TG_GRP * grp + jj;
+        const bool act = jj < TG_GRP && e < b.E;
         // the bulk stores of the previous group have finished reading their staging areas (the A regions)
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
         // ---- coordinates and solution of the group -> the (still unused) gradient area: [jj] 48 : x[8][3], u[8][3]
+        // (a register software pipeline of these gathers was measured: the compiler spills the prefetched values, 19.2 -> 20.9 ms)
         if (act) {
             const int64_t v = b.conn[e * 8 + qq];
             double* xd = Gw + jj * 48 + qq * 3;
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
                 const double xv = x_vd[v * 3 + d];
-                const double uv = tg_load_u(u, mask, values, v * 3 + d);
+                double uv = u[v * 3 + d];
+                if (mask) {
+                    const double m = mask[v * 3 + d];
+                    uv = (1.0 - m) * uv + m * values[v * 3 + d];
+                }
                 xd[d] = xv;
                 xd[24 + d] = hyper ? uv + xv : uv;
             }
@@ -126,9 +180,18 @@ k_tangent_general_mma(feb200_batch b, const double* __restrict__ x_vd, const dou
             double* gd = Gw + jj * TG_GE + qq * TG_GQ;
 #pragma unroll
             for (int i = 0; i < 24; ++i) gd[i] = g[i];
+        }
+        // ---- per sub-group of AGRP elements: their w A_q -> shared memory, then phase 2 for them
+#pragma unroll 1
+        for (int sub = 0; sub < TG_GRP / TG_AGRP; ++sub) {
+        if (sub > 0) {                  // the staged K_e of the previous sub-group has left the A area
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+        }
+        if (act && jj / TG_AGRP == sub) {
             int qs;
             const double* mp = mp_of(b, e, qs);
-            double* ad = Aw + jj * TG_AE + qq * TG_AQ;
+            double* ad = Aw + (jj % TG_AGRP) * TG_AE + qq * TG_AQ;
             if (b.material == MAT_SVK) {
                 // point_tangent's closed form with the isotropic C written out:
                 // A[(i,d),(k,l)] = lam delta_id F[k][l] + mu (delta_il F[k][d] + delta_dl F[k][i]),  F = H
@@ -160,42 +223,56 @@ k_tangent_general_mma(feb200_batch b, const double* __restrict__ x_vd, const dou
         __syncwarp();
         // ---- phase 2: the nine 8 x 8 x 24 products of every element of the group
 #pragma unroll 1
-        for (int jv = 0; jv < 4; ++jv) {
-            const int64_t ev = 4 * grp + jv;
+        for (int jv = sub * TG_AGRP; jv < (sub + 1) * TG_AGRP; ++jv) {
+            const int64_t ev = TG_GRP * grp + jv;
             if (ev >= b.E) break;
             const double* Ge = Gw + jv * TG_GE;
-            double* Ae = Aw + jv * TG_AE;
-            double C[3][3][2];
+            double* Ae = Aw + (jv % TG_AGRP) * TG_AE;
+            double C[9][2];
 #pragma unroll
-            for (int d = 0; d < 3; ++d)
+            for (int dk = 0; dk < 9; ++dk) C[dk][0] = C[dk][1] = 0.0;
 #pragma unroll
-                for (int k = 0; k < 3; ++k) C[d][k][0] = C[d][k][1] = 0.0;
+            for (int h = 0; h < 2; ++h) {
+                double Y[4][5][2];
+                auto product1 = [&](int r) {                                // Y[r][nt] = g_q A_q^T, q = 4 h + r
+                    const int q = 4 * h + r;
+                    double a1 = Ge[q * TG_GQ + offA1];
+                    if (tig == 3) a1 = 0.0;
+                    const double* Aq = Ae + q * TG_AQ + io27[r];
 #pragma unroll
-            for (int s = 0; s < 6; ++s) {
-                const double g0 = Ge[offG[s]], g1 = Ge[offG[s] + 1], g2 = Ge[offG[s] + 2];
-                const double aop = isel[s] == 0 ? g0 : (isel[s] == 1 ? g1 : g2);
-                const double* row = Ae + offA[s];
-#pragma unroll
-                for (int d = 0; d < 3; ++d)
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const double* r = row + d * 9 + k * 3;
-                        const double y = r[0] * g0 + r[1] * g1 + r[2] * g2;
-                        dmma884(C[d][k][0], C[d][k][1], aop, y);
+                    for (int nt = 0; nt < 5; ++nt) {
+                        Y[r][nt][0] = Y[r][nt][1] = 0.0;
+                        dmma884(Y[r][nt][0], Y[r][nt][1], a1, Aq[cB[nt]]);
                     }
+                };
+                auto product2 = [&](int st, bool sel, int ra, int rb) {     // slot value: sel ? Y[ra] : Y[rb]
+                    const double aop = Ge[offAop[3 * h + st]];
+#pragma unroll
+                    for (int dk = 0; dk < 9; ++dk) {
+                        const double y = sel ? Y[ra][dk >> 1][dk & 1] : Y[rb][dk >> 1][dk & 1];
+                        dmma884(C[dk][0], C[dk][1], aop, y);
+                    }
+                };
+                product1(0);
+                product1(1);
+                product2(0, sel0, 1, 0);
+                product1(2);
+                product2(1, sel1, 2, 1);
+                product1(3);
+                product2(2, sel2, 2, 3);
             }
             __syncwarp();                                                   // all lanes are done with A of this element
             // ---- stage K_e[(a)][b][3][3] (a = gid, b = 2 tig, 2 tig + 1) where A lived, then one bulk store
             double2* st = reinterpret_cast<double2*>(Ae + (gid * 8 + 2 * tig) * 9);
-            st[0] = make_double2(C[0][0][0], C[0][1][0]);
-            st[1] = make_double2(C[0][2][0], C[1][0][0]);
-            st[2] = make_double2(C[1][1][0], C[1][2][0]);
-            st[3] = make_double2(C[2][0][0], C[2][1][0]);
-            st[4] = make_double2(C[2][2][0], C[0][0][1]);
-            st[5] = make_double2(C[0][1][1], C[0][2][1]);
-            st[6] = make_double2(C[1][0][1], C[1][1][1]);
-            st[7] = make_double2(C[1][2][1], C[2][0][1]);
-            st[8] = make_double2(C[2][1][1], C[2][2][1]);
+            st[0] = make_double2(C[0][0], C[1][0]);
+            st[1] = make_double2(C[2][0], C[3][0]);
+            st[2] = make_double2(C[4][0], C[5][0]);
+            st[3] = make_double2(C[6][0], C[7][0]);
+            st[4] = make_double2(C[8][0], C[0][1]);
+            st[5] = make_double2(C[1][1], C[2][1]);
+            st[6] = make_double2(C[3][1], C[4][1]);
+            st[7] = make_double2(C[5][1], C[6][1]);
+            st[8] = make_double2(C[7][1], C[8][1]);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) {
@@ -205,6 +282,7 @@ k_tangent_general_mma(feb200_batch b, const double* __restrict__ x_vd, const dou
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         }
+        }   // sub-group
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     __syncwarp();
@@ -222,7 +300,7 @@ int tangent_general_mma(cudaStream_t st, const feb200_batch& b, const double* x_
         FEB_CUDA(cudaFuncSetAttribute(k_tangent_general_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    const int64_t want = ceil_div(ceil_div(b.E, 4), FEB_TG_WARPS);
+    const int64_t want = ceil_div(ceil_div(b.E, TG_GRP), FEB_TG_WARPS);
     const int grid = (int)(want < sm_count() ? want : sm_count());
     k_tangent_general_mma<<<grid, FEB_TG_WARPS * 32, smem, st>>>(b, x_vd, u, mask, values, K_e);
     return FEB200_OK;

@@ -45,11 +45,16 @@ def timed(fn, reps=reps):
 tangent = lambda: _lib.call("feb200_element_tangent", b, _lib.ptr(ebc._vertices), _lib.ptr(u), None, None, _lib.ptr(K_e))
 gather = lambda: _lib.call("feb200_assemble_csr", plan.maps[0], pat.V, pat.U, _lib.ptr(K_e), _lib.ptr(plan.slot_rank[0]),
                            _lib.ptr(pat.nindptr), pat.max_deg, _lib.ptr(vals), 0, None, None)
+mask = torch.zeros_like(u); mask[:3000] = 1.0
+dvals = torch.zeros_like(u)
+tangent_m = lambda: _lib.call("feb200_element_tangent", b, _lib.ptr(ebc._vertices), _lib.ptr(u), _lib.ptr(mask), _lib.ptr(dvals), _lib.ptr(K_e))
 which = "scalar" if os.environ.get("FEB200_TANGENT_SCALAR") else "tensor-core"
 E = ebc.E[0]
 for rep in range(2):
     t = timed(tangent)
     print(f"{model} n={n} element_tangent ({which}) {t:8.3f} ms   {E / t / 1e3:9.1f} M elements/s   K_e write {E * 4608 / t / 1e6:7.0f} GB/s")
+    t = timed(tangent_m)
+    print(f"{model} n={n} element_tangent, Dirichlet blend on the fly {t:8.3f} ms")
     t = timed(gather)
     print(f"{model} n={n} assemble_csr               {t:8.3f} ms   {(E * 4608 + pat.nnz * 8) / t / 1e6:7.0f} GB/s")
     t = timed(lambda: _lib.call("feb200_element_residual", b, _lib.ptr(ebc._vertices), _lib.ptr(u), None, None, _lib.ptr(R_e)))
