@@ -531,7 +531,7 @@ def main():
         ms_h, _ = timed(runh.assembly_step, max(2, args.steps // 2), 2)
         nb = runh.newton_block(args.cg_iters, args.steps, ms_h,
                                "BASELINE configs[2]: hyperelastic (St. Venant-Kirchhoff) Newton-CG step on the same global mesh, "
-                               "generic two-pass assembly (state-dependent tangent), fixed CG iteration count")
+                               "two-pass assembly (tensor-core element tangent k_tangent_general_mma -> K_e in HBM -> row-panel gather), fixed CG iteration count")
         nb["assembly_ms"] = ms_h
         nb["assembly_elements_per_s"] = total_E / (ms_h * 1e-3)
         extra["newton_cg_hyperelastic"] = nb

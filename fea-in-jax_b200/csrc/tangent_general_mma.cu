@@ -24,6 +24,8 @@
 //            K[a][2t+1] = 144 contiguous bytes of K_e[(e*8 + a)][b][3][3];
 //   store    the element's 4608 bytes are staged in the shared memory its A_q occupied and leave as ONE bulk asynchronous
 //            copy (cp.async.bulk shared -> global), overlapping the next element's products.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "element_math.cuh"
 #include "hex8_mma.cuh"
@@ -33,6 +35,12 @@
 #endif
 #ifndef FEB_TG_GROUP
 #define FEB_TG_GROUP 4                    /* elements per group (lanes 8 * GROUP .. 31 idle in phase 1 when < 4) */
+#endif
+#ifndef FEB_TG_NOSTORE
+#define FEB_TG_NOSTORE 0                  /* 1 = timing experiment: K_e never leaves the SM */
+#endif
+#ifndef FEB_TG_PAIR
+#define FEB_TG_PAIR 1                     /* 1 = phase 2 runs two elements as one instruction stream */
 #endif
 #ifndef FEB_TG_AGROUP
 #define FEB_TG_AGROUP 2                   /* elements of a group whose point tangents w A_q sit in shared memory at a time: the
@@ -51,6 +59,8 @@ constexpr int TG_DPHI = 26;               // doubles per point of the basis tabl
 constexpr size_t TG_TABLE = (size_t)(8 * TG_DPHI + 8) * 8;
 constexpr int TG_GRP = FEB_TG_GROUP;
 constexpr int TG_AGRP = FEB_TG_AGROUP;    // elements whose w A_q is resident at a time
+constexpr int TG_NP = FEB_TG_PAIR ? 2 : 1; // elements per instruction stream in phase 2
+static_assert(TG_AGRP % TG_NP == 0, "FEB_TG_PAIR needs an even FEB_TG_AGROUP");
 static_assert(TG_GRP % TG_AGRP == 0, "FEB_TG_AGROUP must divide FEB_TG_GROUP");
 constexpr size_t TG_PER_WARP = (size_t)(TG_GRP * TG_GE + TG_AGRP * TG_AE) * 8;
 
@@ -221,36 +231,48 @@ k_tangent_general_mma(feb200_batch b, const double* __restrict__ x_vd, const dou
             }
         }
         __syncwarp();
-        // ---- phase 2: the nine 8 x 8 x 24 products of every element of the group
+        // ---- phase 2: the chained products of the sub-group's elements, NP elements per instruction stream (two independent
+        //      load -> DMMA -> select -> DMMA chains keep the FP64 tensor pipe busy from one warp)
 #pragma unroll 1
-        for (int jv = sub * TG_AGRP; jv < (sub + 1) * TG_AGRP; ++jv) {
+        for (int jv = sub * TG_AGRP; jv < (sub + 1) * TG_AGRP; jv += TG_NP) {
             const int64_t ev = TG_GRP * grp + jv;
             if (ev >= b.E) break;
-            const double* Ge = Gw + jv * TG_GE;
-            double* Ae = Aw + (jv % TG_AGRP) * TG_AE;
-            double C[9][2];
+            const double* Ge[TG_NP];
+            double* Ae[TG_NP];
+            double C[TG_NP][9][2];
 #pragma unroll
-            for (int dk = 0; dk < 9; ++dk) C[dk][0] = C[dk][1] = 0.0;
+            for (int p = 0; p < TG_NP; ++p) {
+                Ge[p] = Gw + (jv + p) * TG_GE;
+                Ae[p] = Aw + ((jv + p) % TG_AGRP) * TG_AE;
+#pragma unroll
+                for (int dk = 0; dk < 9; ++dk) C[p][dk][0] = C[p][dk][1] = 0.0;
+            }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                double Y[4][5][2];
+                double Y[TG_NP][4][5][2];
                 auto product1 = [&](int r) {                                // Y[r][nt] = g_q A_q^T, q = 4 h + r
                     const int q = 4 * h + r;
-                    double a1 = Ge[q * TG_GQ + offA1];
-                    if (tig == 3) a1 = 0.0;
-                    const double* Aq = Ae + q * TG_AQ + io27[r];
 #pragma unroll
-                    for (int nt = 0; nt < 5; ++nt) {
-                        Y[r][nt][0] = Y[r][nt][1] = 0.0;
-                        dmma884(Y[r][nt][0], Y[r][nt][1], a1, Aq[cB[nt]]);
+                    for (int p = 0; p < TG_NP; ++p) {
+                        double a1 = Ge[p][q * TG_GQ + offA1];
+                        if (tig == 3) a1 = 0.0;
+                        const double* Aq = Ae[p] + q * TG_AQ + io27[r];
+#pragma unroll
+                        for (int nt = 0; nt < 5; ++nt) {
+                            Y[p][r][nt][0] = Y[p][r][nt][1] = 0.0;
+                            dmma884(Y[p][r][nt][0], Y[p][r][nt][1], a1, Aq[cB[nt]]);
+                        }
                     }
                 };
                 auto product2 = [&](int st, bool sel, int ra, int rb) {     // slot value: sel ? Y[ra] : Y[rb]
-                    const double aop = Ge[offAop[3 * h + st]];
 #pragma unroll
-                    for (int dk = 0; dk < 9; ++dk) {
-                        const double y = sel ? Y[ra][dk >> 1][dk & 1] : Y[rb][dk >> 1][dk & 1];
-                        dmma884(C[dk][0], C[dk][1], aop, y);
+                    for (int p = 0; p < TG_NP; ++p) {
+                        const double aop = Ge[p][offAop[3 * h + st]];
+#pragma unroll
+                        for (int dk = 0; dk < 9; ++dk) {
+                            const double y = sel ? Y[p][ra][dk >> 1][dk & 1] : Y[p][rb][dk >> 1][dk & 1];
+                            dmma884(C[p][dk][0], C[p][dk][1], aop, y);
+                        }
                     }
                 };
                 product1(0);
@@ -261,24 +283,31 @@ k_tangent_general_mma(feb200_batch b, const double* __restrict__ x_vd, const dou
                 product1(3);
                 product2(2, sel2, 2, 3);
             }
-            __syncwarp();                                                   // all lanes are done with A of this element
-            // ---- stage K_e[(a)][b][3][3] (a = gid, b = 2 tig, 2 tig + 1) where A lived, then one bulk store
-            double2* st = reinterpret_cast<double2*>(Ae + (gid * 8 + 2 * tig) * 9);
-            st[0] = make_double2(C[0][0], C[1][0]);
-            st[1] = make_double2(C[2][0], C[3][0]);
-            st[2] = make_double2(C[4][0], C[5][0]);
-            st[3] = make_double2(C[6][0], C[7][0]);
-            st[4] = make_double2(C[8][0], C[0][1]);
-            st[5] = make_double2(C[1][1], C[2][1]);
-            st[6] = make_double2(C[3][1], C[4][1]);
-            st[7] = make_double2(C[5][1], C[6][1]);
-            st[8] = make_double2(C[7][1], C[8][1]);
+            __syncwarp();                                                   // all lanes are done with A of these elements
+            // ---- stage K_e[(a)][b][3][3] (a = gid, b = 2 tig, 2 tig + 1) where A lived, then one bulk store per element
+#pragma unroll
+            for (int p = 0; p < TG_NP; ++p) {
+                double2* st = reinterpret_cast<double2*>(Ae[p] + (gid * 8 + 2 * tig) * 9);
+                st[0] = make_double2(C[p][0][0], C[p][1][0]);
+                st[1] = make_double2(C[p][2][0], C[p][3][0]);
+                st[2] = make_double2(C[p][4][0], C[p][5][0]);
+                st[3] = make_double2(C[p][6][0], C[p][7][0]);
+                st[4] = make_double2(C[p][8][0], C[p][0][1]);
+                st[5] = make_double2(C[p][1][1], C[p][2][1]);
+                st[6] = make_double2(C[p][3][1], C[p][4][1]);
+                st[7] = make_double2(C[p][5][1], C[p][6][1]);
+                st[8] = make_double2(C[p][7][1], C[p][8][1]);
+            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) {
-                const unsigned src = (unsigned)__cvta_generic_to_shared(Ae);
-                double* dst = K_e + ev * 576;
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 4608;" ::"l"(dst), "r"(src) : "memory");
+#pragma unroll
+                for (int p = 0; p < TG_NP; ++p)
+                    if (ev + p < b.E && !FEB_TG_NOSTORE) {
+                        const unsigned src = (unsigned)__cvta_generic_to_shared(Ae[p]);
+                        double* dst = K_e + (ev + p) * 576;
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 4608;" ::"l"(dst), "r"(src) : "memory");
+                    }
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         }
@@ -294,15 +323,22 @@ int tangent_general_mma(cudaStream_t st, const feb200_batch& b, const double* x_
                         const double* values, double* K_e) {
     if (!(b.D == 3 && b.N == 8 && b.Q == 8)) return FEB200_ERR_UNSUPPORTED;
     if (((uintptr_t)K_e & 15) != 0) return FEB200_ERR_UNSUPPORTED;          // bulk stores need 16-byte aligned rows
-    const size_t smem = TG_TABLE + (size_t)FEB_TG_WARPS * TG_PER_WARP;
+    static int warps = 0;                                                   // FEB200_TG_WARPS: fewer workers per SM (profile drivers)
+    if (warps == 0) {
+        const char* env = getenv("FEB200_TG_WARPS");
+        warps = env ? atoi(env) : FEB_TG_WARPS;
+        if (warps < 1 || warps > FEB_TG_WARPS) warps = FEB_TG_WARPS;
+    }
+    const size_t smem = TG_TABLE + (size_t)warps * TG_PER_WARP;
     static bool attr_set = false;
     if (!attr_set) {
-        FEB_CUDA(cudaFuncSetAttribute(k_tangent_general_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FEB_CUDA(cudaFuncSetAttribute(k_tangent_general_mma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(TG_TABLE + (size_t)FEB_TG_WARPS * TG_PER_WARP)));
         attr_set = true;
     }
-    const int64_t want = ceil_div(ceil_div(b.E, TG_GRP), FEB_TG_WARPS);
+    const int64_t want = ceil_div(ceil_div(b.E, TG_GRP), warps);
     const int grid = (int)(want < sm_count() ? want : sm_count());
-    k_tangent_general_mma<<<grid, FEB_TG_WARPS * 32, smem, st>>>(b, x_vd, u, mask, values, K_e);
+    k_tangent_general_mma<<<grid, warps * 32, smem, st>>>(b, x_vd, u, mask, values, K_e);
     return FEB200_OK;
 }
 

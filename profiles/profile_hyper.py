@@ -59,6 +59,19 @@ for rep in range(2):
     print(f"{model} n={n} assemble_csr               {t:8.3f} ms   {(E * 4608 + pat.nnz * 8) / t / 1e6:7.0f} GB/s")
     t = timed(lambda: _lib.call("feb200_element_residual", b, _lib.ptr(ebc._vertices), _lib.ptr(u), None, None, _lib.ptr(R_e)))
     print(f"{model} n={n} element_residual           {t:8.3f} ms")
+if os.environ.get("FEB200_OVERLAP"):
+    # feasibility of running the two passes concurrently (FP64-bound tangent kernel, HBM-bound gather): both on all elements /
+    # vertices at once on two streams (the values are garbage; only the time counts)
+    sb = torch.cuda.Stream()
+    def both():
+        ev = torch.cuda.Event(); ev.record()
+        tangent()
+        with torch.cuda.stream(sb):
+            sb.wait_event(ev)
+            gather()
+        torch.cuda.current_stream().wait_stream(sb)
+    for rep in range(2):
+        print(f"{model} n={n} tangent || gather on two streams {timed(both):8.3f} ms  (FEB200_TG_WARPS={os.environ.get('FEB200_TG_WARPS')})")
 if not os.environ.get("FEB200_TANGENT_SCALAR") and n <= 64:
     tangent(); torch.cuda.synchronize()
     ref = subprocess.run([sys.executable, __file__, str(n), model, "1"], env=dict(os.environ, FEB200_TANGENT_SCALAR="1", FEB200_DUMP="1"),

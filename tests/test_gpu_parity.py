@@ -210,6 +210,24 @@ def test_unstructured_element_order(fj):
     assert rel_err(fj.calculate_residual_wo_dirichlet(token, ebc, maps, u)[0], prob.residual_wo_dirichlet(u)) <= ASM_RTOL
 
 
+def test_two_pass_streaming_gather_with_more_than_eight_slots_per_vertex(fj):
+    # every cell twice (valence 16 at interior vertices): the streaming gather of feb200_assemble_csr takes its first 8 slots
+    # through the cp.async pipeline and the rest through plain loads; state-dependent law -> tensor-core element tangent
+    pts, cells = lattice_mesh("hexahedron", 1, 3, seed=5)
+    cells = np.concatenate([cells, cells[::-1]], axis=0)
+    mp = np.array([1.0e6, 0.3])
+    ebc, maps, token, prob, _ = build_pair(fj, pts, [dict(cell="hexahedron", degree=1, qdeg=2, cells=cells,
+                                                         model="st_venant_kirchhoff", mp=mp)])
+    u = 1e-2 * np.random.default_rng(2).normal(size=pts.size)
+    before = _lib_launches(fj)
+    J = fj.calculate_jacobian_wo_dirichlet(token, ebc, maps, u, None)
+    d_o, r_o, c_o = prob.jacobian_wo_dirichlet(u)
+    assert np.array_equal(np_(J.row), r_o) and np.array_equal(np_(J.col), c_o) and rel_err(J.data, d_o) <= ASM_RTOL
+    after = _lib_launches(fj)
+    assert after.get("feb200_element_tangent", 0) > before.get("feb200_element_tangent", 0)
+    assert after.get("feb200_assemble_csr", 0) > before.get("feb200_assemble_csr", 0)
+
+
 # ------------------------------------------------------------------------------------------ Dirichlet + sparse helpers
 def _hex_bvp(fj, n, layout="EQM", model="elastic_isotropic"):
     Vx, cells, u, mp, bcs, vals = orc.synthetic_hex_problem(n, material_layout=layout)
