@@ -26,28 +26,32 @@ template <int U>
 __device__ __forceinline__ void store_panel(int lane, int64_t a, int deg, int64_t p0, const double* acc,
                                             double* __restrict__ values, int accumulate,
                                             const int32_t* __restrict__ nindices, const double* __restrict__ mask,
-                                            unsigned char* flags) {
+                                            const uint8_t* __restrict__ vflags, unsigned char* flags) {
     constexpr int U2 = U * U;
     const int row_len = U * deg;
     double* dst = values + (int64_t)U2 * p0;
-    if (mask) {
+    const bool elim = mask || vflags;
+    if (elim) {
         for (int r = lane; r < deg; r += 32) {
             const int64_t colv = nindices[p0 + r];
             unsigned int f = (colv == a) ? 0x80u : 0u;
+            if (vflags) f |= (unsigned int)vflags[colv] & ((1u << U) - 1u);
+            else {
 #pragma unroll
-            for (int j = 0; j < U; ++j) f |= (mask[colv * U + j] != 0.0) ? (1u << j) : 0u;
+                for (int j = 0; j < U; ++j) f |= (mask[colv * U + j] != 0.0) ? (1u << j) : 0u;
+            }
             flags[r] = (unsigned char)f;
         }
         __syncwarp();
     }
 #pragma unroll
     for (int i = 0; i < U; ++i) {                       // row by row: no division by the run-time row length
-        const bool rm = mask ? (mask[a * U + i] != 0.0) : false;
+        const bool rm = vflags ? (((unsigned int)vflags[a] >> i) & 1u) : (mask ? (mask[a * U + i] != 0.0) : false);
         for (int c = lane; c < row_len; c += 32) {
             const int t = i * row_len + c;
             double v = acc[t];
             if (accumulate) v += dst[t];
-            if (mask) {
+            if (elim) {
                 const int r = c / U, j = c - r * U;
                 const unsigned int f = flags[r];
                 const bool cm = (f >> j) & 1u;
@@ -64,7 +68,8 @@ template <int U>
 __global__ void k_assemble_csr(const unsigned long long* __restrict__ row_ind, const unsigned long long* __restrict__ col_ind,
                                int64_t V, int N, const double* __restrict__ K_e, const uint16_t* __restrict__ slot_rank,
                                const int64_t* __restrict__ nindptr, int max_deg, double* __restrict__ values, int accumulate,
-                               const int32_t* __restrict__ nindices, const double* __restrict__ mask) {
+                               const int32_t* __restrict__ nindices, const double* __restrict__ mask,
+                               const uint8_t* __restrict__ vflags) {
     constexpr int U2 = U * U;
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -90,7 +95,7 @@ __global__ void k_assemble_csr(const unsigned long long* __restrict__ row_ind, c
             }
             __syncwarp();
         }
-        store_panel<U>(lane, a, deg, p0, acc, values, accumulate, nindices, mask, flags);
+        store_panel<U>(lane, a, deg, p0, acc, values, accumulate, nindices, mask, vflags, flags);
         __syncwarp();
     }
 }
@@ -106,7 +111,8 @@ __global__ void __launch_bounds__(256, 4) k_assemble_csr_pre(const unsigned long
                                                           const int64_t* __restrict__ nindptr, int max_deg,
                                                           double* __restrict__ values, int accumulate,
                                                           const int32_t* __restrict__ nindices,
-                                                          const double* __restrict__ mask) {
+                                                          const double* __restrict__ mask,
+                                                          const uint8_t* __restrict__ vflags) {
     constexpr int U2 = U * U;
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -147,7 +153,7 @@ __global__ void __launch_bounds__(256, 4) k_assemble_csr_pre(const unsigned long
                 __syncwarp();
             }
         }
-        store_panel<U>(lane, a, deg, p0, acc, values, accumulate, nindices, mask, flags);
+        store_panel<U>(lane, a, deg, p0, acc, values, accumulate, nindices, mask, vflags, flags);
         __syncwarp();
     }
 }
@@ -179,7 +185,8 @@ __global__ void __launch_bounds__(AS_WARPS * 32, 1)
 k_assemble_hex8_stream(const unsigned long long* __restrict__ row_ind, const unsigned long long* __restrict__ col_ind, int64_t V,
                        const double* __restrict__ K_e, const uint16_t* __restrict__ slot_rank,
                        const int64_t* __restrict__ nindptr, double* __restrict__ values,
-                       const int32_t* __restrict__ nindices, const double* __restrict__ mask) {
+                       const int32_t* __restrict__ nindices, const double* __restrict__ mask,
+                       const uint8_t* __restrict__ vflags) {
     extern __shared__ __align__(16) unsigned char as_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* my = as_smem + (size_t)warp * AS_NB * AS_BUF;
@@ -213,14 +220,45 @@ k_assemble_hex8_stream(const unsigned long long* __restrict__ row_ind, const uns
         asm volatile("cp.async.commit_group;" ::: "memory");               // always: the group count stays uniform
     };
 
+    // Dirichlet elimination: neighbour id (two vertices ahead) and the mask entries of the neighbour / of the row vertex
+    // (one vertex ahead) are prefetched into registers like the slot ids, so nothing is gathered at store time
+    auto load_nb = [&](int64_t k, int64_t meta) -> int {
+        const int64_t p0 = __shfl_sync(0xffffffffu, meta, 2), p1 = __shfl_sync(0xffffffffu, meta, 3);
+        return (ELIM && k < n_mine && p0 + lane < p1) ? nindices[p0 + lane] : -1;
+    };
+    auto load_mask = [&](int64_t k, int nb, double (&mk)[3], double& rowm, unsigned& fb, unsigned& frow) {
+        mk[0] = mk[1] = mk[2] = 0.0;
+        rowm = 0.0;
+        fb = frow = 0u;
+        if (ELIM && k < n_mine) {
+            if (vflags) {                       // one byte per vertex instead of three doubles
+                if (nb >= 0) fb = vflags[nb];
+                if (lane == 0) frow = vflags[w0 + k * W];
+            } else {
+                if (nb >= 0) {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) mk[j] = mask[(int64_t)nb * 3 + j];
+                }
+                if (lane < 3) rowm = mask[(w0 + k * W) * 3 + lane];
+            }
+        }
+    };
     int64_t meta0 = load_meta(0), meta1 = load_meta(1), meta2 = load_meta(2), meta3 = load_meta(3);
     int64_t sl0 = load_slot(0, meta0), sl1 = load_slot(1, meta1), sl2 = load_slot(2, meta2);
+    int nb0 = load_nb(0, meta0), nb1 = load_nb(1, meta1);
+    double mk0[3], rowm0;
+    unsigned fb0, frow0;
+    load_mask(0, nb0, mk0, rowm0, fb0, frow0);
     issue(0, meta0, sl0);
     issue(1, meta1, sl1);
     for (int64_t k = 0; k < n_mine; ++k) {
         issue(k + 2, meta2, sl2);
         const int64_t sl3 = load_slot(k + 3, meta3);
         const int64_t meta4 = load_meta(k + 4);
+        const int nb2 = load_nb(k + 2, meta2);
+        double mk1[3], rowm1;
+        unsigned fb1, frow1;
+        load_mask(k + 1, nb1, mk1, rowm1, fb1, frow1);
         asm volatile("cp.async.wait_group 2;" ::: "memory");              // the group of vertex k has landed
         __syncwarp();
         const int64_t a = w0 + k * W;
@@ -256,6 +294,11 @@ k_assemble_hex8_stream(const unsigned long long* __restrict__ row_ind, const uns
                 for (int c = 0; c < 9; ++c) acc[c] += __ldcs(K_e + slot * 72 + src * 9 + c);
             }
         }
+        bool rm3[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            rm3[i] = ELIM && (vflags ? ((__shfl_sync(0xffffffffu, frow0, 0) >> i) & 1u) != 0u
+                                                : __shfl_sync(0xffffffffu, rowm0, i) != 0.0);
         if (lane < deg) {
             double* dst = values + 9 * p0 + 3 * lane;
             const int64_t row_len = 3 * (int64_t)deg;
@@ -266,15 +309,17 @@ k_assemble_hex8_stream(const unsigned long long* __restrict__ row_ind, const uns
                     for (int j = 0; j < 3; ++j) acc[i * 3 + j] += __ldcs(dst + i * row_len + j);
             }
             if (ELIM) {
-                const int64_t nb = nindices[p0 + lane];
+                // (per-block flag rows fetched with the row blocks, as the sweep kernel uses them, were measured: no difference)
+                const unsigned cf = vflags ? (fb0 & 7u)
+                                           : ((mk0[0] != 0.0 ? 1u : 0u) | (mk0[1] != 0.0 ? 2u : 0u) | (mk0[2] != 0.0 ? 4u : 0u));
+                const unsigned rf = (rm3[0] ? 1u : 0u) | (rm3[1] ? 2u : 0u) | (rm3[2] ? 4u : 0u);
+                const bool diag = (nb0 == a);
+                if (cf | rf) {
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const bool rm = mask[a * 3 + i] != 0.0;
+                    for (int i = 0; i < 3; ++i)
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) {
-                        const bool cm = mask[nb * 3 + j] != 0.0;
-                        if (rm || cm) acc[i * 3 + j] = (rm && nb == a && i == j) ? 1.0 : 0.0;
-                    }
+                        for (int j = 0; j < 3; ++j)
+                            if (((rf >> i) & 1u) || ((cf >> j) & 1u)) acc[i * 3 + j] = (((rf >> i) & 1u) && diag && i == j) ? 1.0 : 0.0;
                 }
             }
 #pragma unroll
@@ -285,6 +330,8 @@ k_assemble_hex8_stream(const unsigned long long* __restrict__ row_ind, const uns
         __syncwarp();                                                      // buffer k % NB is free for vertex k + 3
         meta0 = meta1; meta1 = meta2; meta2 = meta3; meta3 = meta4;
         sl0 = sl1; sl1 = sl2; sl2 = sl3;
+        nb0 = nb1; nb1 = nb2;
+        mk0[0] = mk1[0]; mk0[1] = mk1[1]; mk0[2] = mk1[2]; rowm0 = rowm1; fb0 = fb1; frow0 = frow1;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
@@ -380,12 +427,12 @@ using namespace feb;
 
 extern "C" {
 
-int feb200_assemble_csr(feb200_stream s, const feb200_batch_map* map, int64_t V, int32_t U, const double* K_e,
-                        const uint16_t* slot_rank, const int64_t* nindptr, int32_t max_deg, double* values,
-                        int32_t accumulate, const int32_t* nindices, const double* mask) {
+static int assemble_csr_impl(feb200_stream s, const feb200_batch_map* map, int64_t V, int32_t U, const double* K_e,
+                             const uint16_t* slot_rank, const int64_t* nindptr, int32_t max_deg, double* values,
+                             int32_t accumulate, const int32_t* nindices, const double* mask, const uint8_t* vflags) {
     FEB_REQUIRE(map && map->row_ind && map->col_ind && K_e && slot_rank && nindptr && values, FEB200_ERR_INVALID,
                 "assemble_csr: null pointer");
-    FEB_REQUIRE(!mask || nindices, FEB200_ERR_INVALID, "assemble_csr: mask given without nindices");
+    FEB_REQUIRE(!(mask || vflags) || nindices, FEB200_ERR_INVALID, "assemble_csr: mask / vertex flags given without nindices");
     FEB_REQUIRE(max_deg > 0 && max_deg <= 65535, FEB200_ERR_INVALID, "assemble_csr: max_deg=%d out of range", max_deg);
     if (V == 0) return FEB200_OK;
     cudaStream_t st = as_stream(s);
@@ -413,9 +460,9 @@ int feb200_assemble_csr(feb200_stream s, const feb200_batch_map* map, int64_t V,
                 FEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));            \
                 attr_set = true;                                                                                       \
             }                                                                                                          \
-            kern<<<(int)gs, AS_WARPS * 32, sm, st>>>(ri, ci, V, K_e, slot_rank, nindptr, values, nindices, mask);      \
+            kern<<<(int)gs, AS_WARPS * 32, sm, st>>>(ri, ci, V, K_e, slot_rank, nindptr, values, nindices, mask, vflags);      \
         }
-        if (mask) { if (accumulate) FEB_AS_STREAM(true, true) else FEB_AS_STREAM(true, false) }
+        if (mask || vflags) { if (accumulate) FEB_AS_STREAM(true, true) else FEB_AS_STREAM(true, false) }
         else { if (accumulate) FEB_AS_STREAM(false, true) else FEB_AS_STREAM(false, false) }
 #undef FEB_AS_STREAM
         FEB_CHECK_LAUNCH("assemble_csr");
@@ -428,12 +475,12 @@ int feb200_assemble_csr(feb200_stream s, const feb200_batch_map* map, int64_t V,
             auto kern = k_assemble_csr_pre<UU, 4>;                                                                     \
             if (smem > 48 * 1024) FEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             kern<<<(int)g, wpb * 32, smem, st>>>(ri, ci, V, map->N, K_e, slot_rank, nindptr, max_deg, values, accumulate, \
-                                                 nindices, mask);                                                      \
+                                                 nindices, mask, vflags);                                              \
         } else {                                                                                                       \
             auto kern = k_assemble_csr<UU>;                                                                            \
             if (smem > 48 * 1024) FEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             kern<<<(int)g, wpb * 32, smem, st>>>(ri, ci, V, map->N, K_e, slot_rank, nindptr, max_deg, values, accumulate, \
-                                                 nindices, mask);                                                      \
+                                                 nindices, mask, vflags);                                              \
         }                                                                                                              \
     }
     if (U == 2) FEB_ASM(2)
@@ -443,6 +490,19 @@ int feb200_assemble_csr(feb200_stream s, const feb200_batch_map* map, int64_t V,
 #undef FEB_ASM
     FEB_CHECK_LAUNCH("assemble_csr");
     return FEB200_OK;
+}
+
+int feb200_assemble_csr(feb200_stream s, const feb200_batch_map* map, int64_t V, int32_t U, const double* K_e,
+                        const uint16_t* slot_rank, const int64_t* nindptr, int32_t max_deg, double* values,
+                        int32_t accumulate, const int32_t* nindices, const double* mask) {
+    return assemble_csr_impl(s, map, V, U, K_e, slot_rank, nindptr, max_deg, values, accumulate, nindices, mask, nullptr);
+}
+
+int feb200_assemble_csr_flags(feb200_stream s, const feb200_batch_map* map, int64_t V, int32_t U, const double* K_e,
+                              const uint16_t* slot_rank, const int64_t* nindptr, int32_t max_deg, double* values,
+                              int32_t accumulate, const int32_t* nindices, const uint8_t* vertex_flags) {
+    FEB_REQUIRE(U <= 7, FEB200_ERR_UNSUPPORTED, "assemble_csr_flags: U=%d does not fit the flag byte", U);
+    return assemble_csr_impl(s, map, V, U, K_e, slot_rank, nindptr, max_deg, values, accumulate, nindices, nullptr, vertex_flags);
 }
 
 int feb200_dirichlet_lhs(feb200_stream s, int64_t V, int32_t U, const int64_t* nindptr, const int32_t* nindices,

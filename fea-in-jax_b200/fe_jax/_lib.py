@@ -91,6 +91,7 @@ SIGNATURES = {
     "feb200_slot_rank": (c_int32, [_P, _P, _I64, _I32, _P, _P, _P]),
     "feb200_pattern_expand": (c_int32, [_P, _I64, _I32, _P, _P, _P, _P, _P]),
     "feb200_assemble_csr": (c_int32, [_P, POINTER(BatchMap), _I64, _I32, _P, _P, _P, _I32, _P, _I32, _P, _P]),
+    "feb200_assemble_csr_flags": (c_int32, [_P, POINTER(BatchMap), _I64, _I32, _P, _P, _P, _I32, _P, _I32, _P, _P]),
     "feb200_fused_smem_bytes": (_SZ, [_I32, _I32]),
     "feb200_assemble_fused_hex8": (c_int32, [_P, POINTER(Batch), POINTER(FusedPlan), _P, _P, _P, _P, _P, _P, _P]),
     "feb200_fused_mma_smem_bytes": (_SZ, [_I32, _I32, _I32]),

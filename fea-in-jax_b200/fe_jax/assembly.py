@@ -429,9 +429,10 @@ def _assemble_values(element_residual_func, ebc, assembly_map_b, u, mask=None, v
                   _lib.ptr(K_e))
         bm = plan.maps[i]
         elim = eliminate and mask is not None and not multi
-        _lib.call("feb200_assemble_csr", bm, pat.V, pat.U, _lib.ptr(K_e), _lib.ptr(plan.slot_rank[i]),
+        # fused elimination from the per-vertex flag bytes (one byte per CSR block instead of U mask doubles)
+        _lib.call("feb200_assemble_csr_flags", bm, pat.V, pat.U, _lib.ptr(K_e), _lib.ptr(plan.slot_rank[i]),
                   _lib.ptr(pat.nindptr), pat.max_deg, _lib.ptr(vals), 1 if multi else 0,
-                  _lib.ptr(pat.nindices) if elim else None, _lib.ptr(mask) if elim else None)
+                  _lib.ptr(pat.nindices) if elim else None, _lib.ptr(_vertex_flags(ebc, mask)) if elim else None)
     if multi and eliminate and mask is not None:
         _lib.call("feb200_dirichlet_lhs", pat.V, pat.U, _lib.ptr(pat.nindptr), _lib.ptr(pat.nindices), _lib.ptr(mask), _lib.ptr(vals))
     return vals, pat

@@ -154,6 +154,11 @@ int feb200_pattern_expand(feb200_stream s, int64_t V, int32_t U, const int64_t* 
 int feb200_assemble_csr(feb200_stream s, const feb200_batch_map* map, int64_t V, int32_t U, const double* K_e,
                         const uint16_t* slot_rank, const int64_t* nindptr, int32_t max_deg, double* values,
                         int32_t accumulate, const int32_t* nindices, const double* mask);
+/* The same with the constraints as one byte per vertex (bit j set when DoF U*v+j is constrained; NULL = no
+ * elimination) instead of the (U*V) mask of doubles: the fused elimination then reads one byte per CSR block. */
+int feb200_assemble_csr_flags(feb200_stream s, const feb200_batch_map* map, int64_t V, int32_t U, const double* K_e,
+                              const uint16_t* slot_rank, const int64_t* nindptr, int32_t max_deg, double* values,
+                              int32_t accumulate, const int32_t* nindices, const uint8_t* vertex_flags);
 /* Fused assembly for linear isotropic hex8 batches (material constant per element): element tangents are
  * computed and summed into the CSR row panels in ONE kernel (K_e never reaches HBM).  The tile plan groups
  * vertices that are close in space; per tile: its vertices, the elements touching them and one packed item per

@@ -48,6 +48,11 @@ gather = lambda: _lib.call("feb200_assemble_csr", plan.maps[0], pat.V, pat.U, _l
 mask = torch.zeros_like(u); mask[:3000] = 1.0
 dvals = torch.zeros_like(u)
 tangent_m = lambda: _lib.call("feb200_element_tangent", b, _lib.ptr(ebc._vertices), _lib.ptr(u), _lib.ptr(mask), _lib.ptr(dvals), _lib.ptr(K_e))
+gather_m = lambda: _lib.call("feb200_assemble_csr", plan.maps[0], pat.V, pat.U, _lib.ptr(K_e), _lib.ptr(plan.slot_rank[0]),
+                             _lib.ptr(pat.nindptr), pat.max_deg, _lib.ptr(vals), 0, _lib.ptr(pat.nindices), _lib.ptr(mask))
+from fe_jax.assembly import _vertex_flags
+gather_f = lambda: _lib.call("feb200_assemble_csr_flags", plan.maps[0], pat.V, pat.U, _lib.ptr(K_e), _lib.ptr(plan.slot_rank[0]),
+                             _lib.ptr(pat.nindptr), pat.max_deg, _lib.ptr(vals), 0, _lib.ptr(pat.nindices), _lib.ptr(_vertex_flags(ebc, mask)))
 which = "scalar" if os.environ.get("FEB200_TANGENT_SCALAR") else "tensor-core"
 E = ebc.E[0]
 for rep in range(2):
@@ -57,6 +62,10 @@ for rep in range(2):
     print(f"{model} n={n} element_tangent, Dirichlet blend on the fly {t:8.3f} ms")
     t = timed(gather)
     print(f"{model} n={n} assemble_csr               {t:8.3f} ms   {(E * 4608 + pat.nnz * 8) / t / 1e6:7.0f} GB/s")
+    t = timed(gather_m)
+    print(f"{model} n={n} assemble_csr, Dirichlet elimination fused (mask doubles) {t:8.3f} ms")
+    t = timed(gather_f)
+    print(f"{model} n={n} assemble_csr_flags, Dirichlet elimination fused (flag bytes) {t:8.3f} ms")
     t = timed(lambda: _lib.call("feb200_element_residual", b, _lib.ptr(ebc._vertices), _lib.ptr(u), None, None, _lib.ptr(R_e)))
     print(f"{model} n={n} element_residual           {t:8.3f} ms")
 if os.environ.get("FEB200_OVERLAP"):

@@ -225,7 +225,7 @@ def test_two_pass_streaming_gather_with_more_than_eight_slots_per_vertex(fj):
     assert np.array_equal(np_(J.row), r_o) and np.array_equal(np_(J.col), c_o) and rel_err(J.data, d_o) <= ASM_RTOL
     after = _lib_launches(fj)
     assert after.get("feb200_element_tangent", 0) > before.get("feb200_element_tangent", 0)
-    assert after.get("feb200_assemble_csr", 0) > before.get("feb200_assemble_csr", 0)
+    assert after.get("feb200_assemble_csr_flags", 0) > before.get("feb200_assemble_csr_flags", 0)
 
 
 # ------------------------------------------------------------------------------------------ Dirichlet + sparse helpers
