@@ -233,6 +233,30 @@ class Problem:
         self.u = self.u_host.to(dev)
 
 
+def hyper_kernel_block(fj, _lib, _vertex_flags, timed, args, runh, prh):
+    """Per-kernel times of the hyperelastic two-pass assembly (N = 1) and the traffic they move."""
+    nb = {}
+    eh, ph = runh.ebc, runh.plan
+    bh = eh._batch_struct(0, fj.physics.resolve_residual(prh.token).kind)
+    Eh = eh.E[0]
+    K_eh, R_eh = eh._buffer("K_e", Eh * 576), eh._buffer("R_e", Eh * 24)
+    hk = {"element_residual": lambda: _lib.call("feb200_element_residual", bh, _lib.ptr(eh._vertices), _lib.ptr(prh.u),
+                                                _lib.ptr(runh.mask), _lib.ptr(runh.values), _lib.ptr(R_eh)),
+          "element_tangent": lambda: _lib.call("feb200_element_tangent", bh, _lib.ptr(eh._vertices), _lib.ptr(prh.u),
+                                               _lib.ptr(runh.mask), _lib.ptr(runh.values), _lib.ptr(K_eh)),
+          "assemble_csr": lambda: _lib.call("feb200_assemble_csr_flags", ph.maps[0], runh.pat.V, runh.pat.U, _lib.ptr(K_eh),
+                                            _lib.ptr(ph.slot_rank[0]), _lib.ptr(runh.pat.nindptr), runh.pat.max_deg,
+                                            _lib.ptr(runh.J_vals), 0, _lib.ptr(runh.pat.nindices),
+                                            _lib.ptr(_vertex_flags(eh, runh.mask)))}
+    nb["kernel_ms"] = {k: timed(f, max(2, args.steps // 2), 1)[0] for k, f in hk.items()}
+    # two-pass traffic per rank: K_e written once and read once, CSR values written, slot ranks (2 bytes per node pair)
+    nnz_h = int(runh.pat.nnz)
+    nb["two_pass_bytes"] = 2 * 4608 * Eh + 8 * nnz_h + 2 * 64 * Eh
+    nb["two_pass_gbs"] = nb["two_pass_bytes"] / ((nb["kernel_ms"]["element_tangent"] + nb["kernel_ms"]["assemble_csr"]) * 1e-3) / 1e9
+    del hk, K_eh, R_eh
+    return nb
+
+
 def main():
     args = parse()
     _protect_stdout()
@@ -535,24 +559,8 @@ def main():
         nb["assembly_ms"] = ms_h
         nb["assembly_elements_per_s"] = total_E / (ms_h * 1e-3)
         # per-kernel times of the hyperelastic pass (the same C-ABI calls the builders make), live with CUDA events
-        eh, ph = runh.ebc, runh.plan
-        bh = eh._batch_struct(0, fj.physics.resolve_residual(prh.token).kind)
-        Eh = eh.E[0]
-        K_eh, R_eh = eh._buffer("K_e", Eh * 576), eh._buffer("R_e", Eh * 24)
-        hk = {"element_residual": lambda: _lib.call("feb200_element_residual", bh, _lib.ptr(eh._vertices), _lib.ptr(prh.u),
-                                                    _lib.ptr(runh.mask), _lib.ptr(runh.values), _lib.ptr(R_eh)),
-              "element_tangent": lambda: _lib.call("feb200_element_tangent", bh, _lib.ptr(eh._vertices), _lib.ptr(prh.u),
-                                                   _lib.ptr(runh.mask), _lib.ptr(runh.values), _lib.ptr(K_eh)),
-              "assemble_csr": lambda: _lib.call("feb200_assemble_csr_flags", ph.maps[0], runh.pat.V, runh.pat.U, _lib.ptr(K_eh),
-                                                _lib.ptr(ph.slot_rank[0]), _lib.ptr(runh.pat.nindptr), runh.pat.max_deg,
-                                                _lib.ptr(runh.J_vals), 0, _lib.ptr(runh.pat.nindices),
-                                                _lib.ptr(_vertex_flags(eh, runh.mask)))}
-        nb["kernel_ms"] = {k: timed(f, max(2, args.steps // 2), 1)[0] for k, f in hk.items()}
-        # two-pass traffic per rank: K_e written once and read once, CSR values written, slot ranks (2 bytes per node pair)
-        nnz_h = int(runh.pat.nnz)
-        nb["two_pass_bytes"] = 2 * 4608 * Eh + 8 * nnz_h + 2 * 64 * Eh
-        nb["two_pass_gbs"] = nb["two_pass_bytes"] / ((nb["kernel_ms"]["element_tangent"] + nb["kernel_ms"]["assemble_csr"]) * 1e-3) / 1e9
-        del hk, K_eh, R_eh
+        if world == 1:
+            nb.update(hyper_kernel_block(fj, _lib, _vertex_flags, timed, args, runh, prh))
         extra["newton_cg_hyperelastic"] = nb
         del runh, prh
         torch.cuda.empty_cache()
