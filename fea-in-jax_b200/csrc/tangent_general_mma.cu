@@ -62,7 +62,7 @@ constexpr int TG_AGRP = FEB_TG_AGROUP;    // elements whose w A_q is resident at
 constexpr int TG_NP = FEB_TG_PAIR ? 2 : 1; // elements per instruction stream in phase 2
 static_assert(TG_AGRP % TG_NP == 0, "FEB_TG_PAIR needs an even FEB_TG_AGROUP");
 static_assert(TG_GRP % TG_AGRP == 0, "FEB_TG_AGROUP must divide FEB_TG_GROUP");
-constexpr size_t TG_PER_WARP = (size_t)(TG_GRP * TG_GE + TG_AGRP * TG_AE) * 8;
+constexpr size_t TG_PER_WARP = (size_t)(TG_GRP * TG_GE + TG_AGRP * TG_AE + TG_GRP * 48) * 8;   // G, w A_q, x / u of the group
 
 // w A_q of any law through forward-mode duals on the constitutive function (element_math.cuh), three directions at a time
 // (the derivatives with respect to H[k][0..2] per pass: 36 live dual components instead of the 90 of point_tangent, which
@@ -104,6 +104,7 @@ k_tangent_general_mma(feb200_batch b, const double* __restrict__ x_vd, const dou
     const int gid = lane >> 2, tig = lane & 3;
     double* Gw = reinterpret_cast<double*>(tg_raw + TG_TABLE + (size_t)warp * TG_PER_WARP);   // [4] GE : [q] GQ : [n][3]
     double* Aw = Gw + TG_GRP * TG_GE;                                            // [4] AE : [q] AQ
+    double* Xw = Aw + TG_AGRP * TG_AE;                                           // [4] 48 : x[8][3], u[8][3] of the group
     for (int i = tid; i < 8 * 24; i += blockDim.x) s_dphi[(i / 24) * TG_DPHI + (i % 24)] = b.dphi[i];
     if (tid < 8) s_w[tid] = b.W[tid];
     __syncthreads();                                                        // the only block-wide barrier
@@ -148,11 +149,11 @@ k_tangent_general_mma(feb200_batch b, const double* __restrict__ x_vd, const dou
         // the bulk stores of the previous group have finished reading their staging areas (the A regions)
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
-        // ---- coordinates and solution of the group -> the (still unused) gradient area: [jj] 48 : x[8][3], u[8][3]
+        // ---- coordinates and solution of the group -> shared memory: [jj] 48 : x[8][3], u[8][3]
         // (a register software pipeline of these gathers was measured: the compiler spills the prefetched values, 19.2 -> 20.9 ms)
         if (act) {
             const int64_t v = b.conn[e * 8 + qq];
-            double* xd = Gw + jj * 48 + qq * 3;
+            double* xd = Xw + jj * 48 + qq * 3;
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
                 const double xv = x_vd[v * 3 + d];
@@ -166,30 +167,54 @@ k_tangent_general_mma(feb200_batch b, const double* __restrict__ x_vd, const dou
             }
         }
         __syncwarp();
-        // ---- phase 1: geometry and H at (element jj, point qq)
-        double g[24], H[3][3], w = 0.0;
+        // ---- phase 1: geometry and H at (element jj, point qq); every gradient goes to shared memory as soon as it exists
+        //      (holding the 24 of them in registers across the stores made ptxas spill them: 88 local-memory accesses per lane)
+        double H[3][3], w = 0.0;
         if (act) {
-            const double dt = hex8_gradients(Gw + jj * 48, s_dphi + qq * TG_DPHI, g);
+            const double2* x2 = reinterpret_cast<const double2*>(Xw + jj * 48);
+            const double2* d2 = reinterpret_cast<const double2*>(s_dphi + qq * TG_DPHI);
+            double dq[24];
+            double J[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {                            // two nodes = three double2 per step
+                const double2 xa = x2[3 * h], xb = x2[3 * h + 1], xc = x2[3 * h + 2];
+                const double2 da = d2[3 * h], db = d2[3 * h + 1], dc = d2[3 * h + 2];
+                const double xx[6] = {xa.x, xa.y, xb.x, xb.y, xc.x, xc.y};
+                dq[6 * h] = da.x; dq[6 * h + 1] = da.y; dq[6 * h + 2] = db.x; dq[6 * h + 3] = db.y; dq[6 * h + 4] = dc.x; dq[6 * h + 5] = dc.y;
+#pragma unroll
+                for (int m = 0; m < 2; ++m)
+#pragma unroll
+                    for (int pp = 0; pp < 3; ++pp)
+#pragma unroll
+                        for (int dd = 0; dd < 3; ++dd) J[pp][dd] += xx[3 * m + dd] * dq[6 * h + 3 * m + pp];
+            }
+            double Ji[3][3];
+            const double dt = inverse(J, Ji);
             w = dt * s_w[qq];
-            const double* ue = Gw + jj * 48 + 24;
+            const double* ue = Xw + jj * 48 + 24;
+            double* gd = Gw + jj * TG_GE + qq * TG_GQ;
 #pragma unroll
             for (int i = 0; i < 3; ++i)
 #pragma unroll
                 for (int d = 0; d < 3; ++d) H[i][d] = 0.0;
 #pragma unroll
-            for (int n = 0; n < 8; ++n)
+            for (int n = 0; n < 8; ++n) {
+                double gn[3];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int pp = 0; pp < 3; ++pp) sacc += Ji[d][pp] * dq[n * 3 + pp];
+                    gn[d] = sacc;
+                    gd[n * 3 + d] = sacc;
+                }
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     const double ui = ue[n * 3 + i];
 #pragma unroll
-                    for (int d = 0; d < 3; ++d) H[i][d] += g[n * 3 + d] * ui;
+                    for (int d = 0; d < 3; ++d) H[i][d] += gn[d] * ui;
                 }
-        }
-        __syncwarp();                                                       // every lane has read x / u: the area becomes G
-        if (act) {
-            double* gd = Gw + jj * TG_GE + qq * TG_GQ;
-#pragma unroll
-            for (int i = 0; i < 24; ++i) gd[i] = g[i];
+            }
         }
         // ---- per sub-group of AGRP elements: their w A_q -> shared memory, then phase 2 for them
 #pragma unroll 1
