@@ -228,6 +228,54 @@ def test_two_pass_streaming_gather_with_more_than_eight_slots_per_vertex(fj):
     assert after.get("feb200_assemble_csr_flags", 0) > before.get("feb200_assemble_csr_flags", 0)
 
 
+@pytest.mark.parametrize("model,layout", [("st_venant_kirchhoff", "EQM"), ("st_venant_kirchhoff", "M"), ("mooney_rivlin", "M"),
+                                          ("elastic_orthotropic", "EM")])
+def test_hyperelastic_two_pass_kernels_through_the_c_abi(fj, model, layout):
+    """hex8, state-dependent law: the tensor-core element tangent (k_tangent_general_mma, groups of 4 elements: 5^3 = 125 leaves a
+    ragged last group) with the Dirichlet blend, against the oracle's tangents of the blended state; the streaming gather with the
+    elimination from flag bytes against the same gather with the mask of doubles (bit-identical) and against the oracle."""
+    from fe_jax import _lib
+    from fe_jax.assembly import _plan, _vertex_flags
+    Vx, cells, u, _, bcs, vals = orc.synthetic_hex_problem(5, material_layout="M")
+    E = cells.shape[0]
+    rng = np.random.default_rng(12)
+    base = {"st_venant_kirchhoff": np.array([1.0e6, 0.3]), "mooney_rivlin": np.array([0.5e6, 0.1e6, 2e-7]),
+            "elastic_orthotropic": np.array([40e9, 10e9, 12e9, 0.25, 0.30, 0.20, 4e9, 3e9, 5e9])}[model]
+    shape = {"M": (), "EM": (E,), "EQM": (E, 8)}[layout]
+    mp = base * (1.0 + 0.2 * rng.uniform(size=shape + (1,))) if shape else base
+    if model != "elastic_orthotropic":
+        u = 20.0 * u
+    ebc, maps, token, prob, _ = build_pair(fj, Vx, [dict(cell="hexahedron", degree=1, qdeg=2, cells=cells, model=model, mp=mp)])
+    dofs, values_g, mask_g = orc.dirichlet_arrays(prob.F, 3, bcs, vals)
+    ud, md, vd = (torch.tensor(a, dtype=torch.float64).cuda() for a in (u, mask_g, values_g))
+    kind = fj.physics.resolve_residual(token).kind
+    b = ebc._batch_struct(0, kind)
+    K_e = torch.empty(E * 576, dtype=torch.float64, device="cuda")
+    _lib.call("feb200_element_tangent", b, _lib.ptr(ebc._vertices), _lib.ptr(ud), _lib.ptr(md), _lib.ptr(vd), _lib.ptr(K_e))
+    uw = (1.0 - mask_g) * u + mask_g * values_g
+    xi, W = orc.get_quadrature("hexahedron", 2)
+    _, dphi = orc.eval_basis_and_derivatives("hexahedron", 1, xi)
+    kname = "linear" if model == "elastic_orthotropic" else "hyper"
+    K_o = orc.element_tangents(kname, model, uw.reshape(-1, 3)[cells], Vx[cells], dphi, orc.weights_as_reference(W, True),
+                               orc.expand_material(mp, E, 8))
+    # K_e[(e, a)][b][d][k]  vs  oracle K[(a, d), (b, k)]
+    K_g = np_(K_e).reshape(E, 8, 8, 3, 3).transpose(0, 1, 3, 2, 4).reshape(E, 24, 24)
+    assert np.abs(K_g - K_o).max() <= 1e-12 * np.abs(K_o).max()
+    plan = _plan(ebc, maps)
+    pat = plan.pattern
+    out_m = torch.empty(pat.nnz, dtype=torch.float64, device="cuda")
+    out_f = torch.empty_like(out_m)
+    _lib.call("feb200_assemble_csr", plan.maps[0], pat.V, pat.U, _lib.ptr(K_e), _lib.ptr(plan.slot_rank[0]), _lib.ptr(pat.nindptr),
+              pat.max_deg, _lib.ptr(out_m), 0, _lib.ptr(pat.nindices), _lib.ptr(md))
+    _lib.call("feb200_assemble_csr_flags", plan.maps[0], pat.V, pat.U, _lib.ptr(K_e), _lib.ptr(plan.slot_rank[0]),
+              _lib.ptr(pat.nindptr), pat.max_deg, _lib.ptr(out_f), 0, _lib.ptr(pat.nindices), _lib.ptr(_vertex_flags(ebc, md)))
+    assert torch.equal(out_m, out_f)
+    d_o, r_o, c_o = prob.jacobian_wo_dirichlet(uw)
+    dw_o = orc.apply_dirichlet_bcs_lhs(d_o, r_o, c_o, dofs)
+    assert rel_err(out_f, dw_o) <= ASM_RTOL
+    assert np.array_equal(np_(out_f) == 1.0, dw_o == 1.0)
+
+
 # ------------------------------------------------------------------------------------------ Dirichlet + sparse helpers
 def _hex_bvp(fj, n, layout="EQM", model="elastic_isotropic"):
     Vx, cells, u, mp, bcs, vals = orc.synthetic_hex_problem(n, material_layout=layout)
