@@ -343,306 +343,12 @@ k_tangent_general_mma(feb200_batch b, const double* __restrict__ x_vd, const dou
 }
 
 
-// ------------------------------------------------------------------------------------------------
-// Warp-specialised variant: the two phases of k_tangent_general_mma are bound by different units (phase 1: LSU wavefronts,
-// 6.9 ms at 200^3 on its own; phase 2: the FP64 tensor pipe, 12.1 ms on its own) and, run by the same warps, simply add up.
-// Here a CTA has 4 teams, one per SM sub-partition: warp t produces (phase 1 of a group of 4 elements into one of two shared-memory
-// stages), warps 4 + t and 8 + t consume (phase 2 of two elements each, K_e staged where A_q lived, bulk store).  Hand-over through
-// mbarriers: full[stage] (32 producer lanes arrive), empty[stage] (64 consumer lanes arrive, lane 0 of a consumer only after
-// its bulk stores have finished reading the stage).
-// ------------------------------------------------------------------------------------------------
-constexpr int WS_TEAMS = 4;
-constexpr size_t WS_STAGE = (size_t)(4 * TG_GE + 4 * TG_AE) * 8;             // G and w A_q of 4 elements
-constexpr size_t WS_TEAM = 2 * WS_STAGE + 4 * 48 * 8;                        // two stages + x / u of the group in flight
-constexpr size_t WS_SMEM = TG_TABLE + WS_TEAMS * WS_TEAM;
-
-__device__ __forceinline__ unsigned ws_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void ws_mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ws_smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void ws_mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ws_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool ws_mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok)
-                 : "r"(ws_smem_u32(bar)), "r"(parity)
-                 : "memory");
-    return ok != 0;
-}
-
-__global__ void __launch_bounds__(3 * WS_TEAMS * 32, 1)
-k_tangent_general_ws(feb200_batch b, const double* __restrict__ x_vd, const double* __restrict__ u,
-                     const double* __restrict__ mask, const double* __restrict__ values, double* __restrict__ K_e) {
-    extern __shared__ __align__(16) unsigned char tg_raw[];
-    __shared__ __align__(8) uint64_t bars[WS_TEAMS][2][2];                  // [team][stage][0 = full, 1 = empty]
-    double* s_dphi = reinterpret_cast<double*>(tg_raw);
-    double* s_w = s_dphi + 8 * TG_DPHI;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int gid = lane >> 2, tig = lane & 3;
-    const int team = warp & 3, role = warp >> 2;                            // role 0 = producer, 1 / 2 = consumers
-    for (int i = tid; i < 8 * 24; i += blockDim.x) s_dphi[(i / 24) * TG_DPHI + (i % 24)] = b.dphi[i];
-    if (tid < 8) s_w[tid] = b.W[tid];
-    if (tid == 0) {
-        for (int t = 0; t < WS_TEAMS; ++t)
-            for (int sg = 0; sg < 2; ++sg) {
-                ws_mbar_init(&bars[t][sg][0], 32);
-                ws_mbar_init(&bars[t][sg][1], 64);
-            }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    unsigned char* tbase = tg_raw + TG_TABLE + (size_t)team * WS_TEAM;
-    double* Xw = reinterpret_cast<double*>(tbase + 2 * WS_STAGE);
-    const int64_t n_groups = (b.E + 3) >> 2;
-    const int64_t n_teams = (int64_t)gridDim.x * WS_TEAMS;
-    const int64_t first = (int64_t)blockIdx.x * WS_TEAMS + team;
-    const int64_t n_mine = first < n_groups ? (n_groups - first + n_teams - 1) / n_teams : 0;
-    const bool hyper = (b.kind == KIND_HYPER);
-
-    if (role == 0) {
-        // ================================================================== producer: phase 1
-        const int jj = lane >> 3, qq = lane & 7;
-        for (int64_t k = 0; k < n_mine; ++k) {
-            const int sg = (int)(k & 1);
-            const int64_t grp = first + k * n_teams;
-            const int64_t e = 4 * grp + jj;
-            const bool act = e < b.E;
-            double* Gw = reinterpret_cast<double*>(tbase + (size_t)sg * WS_STAGE);
-            double* Aw = Gw + 4 * TG_GE;
-            if (act) {
-                const int64_t v = b.conn[e * 8 + qq];
-                double* xd = Xw + jj * 48 + qq * 3;
-#pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    const double xv = x_vd[v * 3 + d];
-                    double uv = u[v * 3 + d];
-                    if (mask) {
-                        const double m = mask[v * 3 + d];
-                        uv = (1.0 - m) * uv + m * values[v * 3 + d];
-                    }
-                    xd[d] = xv;
-                    xd[24 + d] = hyper ? uv + xv : uv;
-                }
-            }
-            __syncwarp();
-            if (k >= 2) {                                                   // both consumers have released this stage
-                const uint32_t par = (uint32_t)(((k >> 1) - 1) & 1);
-                while (!ws_mbar_try_wait(&bars[team][sg][1], par)) {}
-            }
-            if (act) {
-                const double2* x2 = reinterpret_cast<const double2*>(Xw + jj * 48);
-                const double2* d2 = reinterpret_cast<const double2*>(s_dphi + qq * TG_DPHI);
-                double dq[24];
-                double J[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
-#pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    const double2 xa = x2[3 * h], xb = x2[3 * h + 1], xc = x2[3 * h + 2];
-                    const double2 da = d2[3 * h], db = d2[3 * h + 1], dc = d2[3 * h + 2];
-                    const double xx[6] = {xa.x, xa.y, xb.x, xb.y, xc.x, xc.y};
-                    dq[6 * h] = da.x; dq[6 * h + 1] = da.y; dq[6 * h + 2] = db.x; dq[6 * h + 3] = db.y; dq[6 * h + 4] = dc.x; dq[6 * h + 5] = dc.y;
-#pragma unroll
-                    for (int m = 0; m < 2; ++m)
-#pragma unroll
-                        for (int pp = 0; pp < 3; ++pp)
-#pragma unroll
-                            for (int dd = 0; dd < 3; ++dd) J[pp][dd] += xx[3 * m + dd] * dq[6 * h + 3 * m + pp];
-                }
-                double Ji[3][3], H[3][3];
-                const double dt = inverse(J, Ji);
-                const double w = dt * s_w[qq];
-                const double* ue = Xw + jj * 48 + 24;
-                double* gd = Gw + jj * TG_GE + qq * TG_GQ;
-#pragma unroll
-                for (int i = 0; i < 3; ++i)
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) H[i][d] = 0.0;
-#pragma unroll
-                for (int n = 0; n < 8; ++n) {
-                    double gn[3];
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) {
-                        double sacc = 0.0;
-#pragma unroll
-                        for (int pp = 0; pp < 3; ++pp) sacc += Ji[d][pp] * dq[n * 3 + pp];
-                        gn[d] = sacc;
-                        gd[n * 3 + d] = sacc;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        const double ui = ue[n * 3 + i];
-#pragma unroll
-                        for (int d = 0; d < 3; ++d) H[i][d] += gn[d] * ui;
-                    }
-                }
-                int qs;
-                const double* mp = mp_of(b, e, qs);
-                double* ad = Aw + jj * TG_AE + qq * TG_AQ;
-                if (b.material == MAT_SVK) {
-                    double lam, mu;
-                    isotropic_lame<3>(mp + (int64_t)qq * qs, lam, mu);
-                    double lF[3][3], mF[3][3];
-#pragma unroll
-                    for (int kk = 0; kk < 3; ++kk)
-#pragma unroll
-                        for (int l = 0; l < 3; ++l) { lF[kk][l] = (w * lam) * H[kk][l]; mF[kk][l] = (w * mu) * H[kk][l]; }
-#pragma unroll
-                    for (int i = 0; i < 3; ++i)
-#pragma unroll
-                        for (int d = 0; d < 3; ++d)
-#pragma unroll
-                            for (int kk = 0; kk < 3; ++kk)
-#pragma unroll
-                                for (int l = 0; l < 3; ++l) {
-                                    double a = 0.0;
-                                    if (i == d) a += lF[kk][l];
-                                    if (i == l) a += mF[kk][d];
-                                    if (d == l) a += mF[kk][i];
-                                    ad[(i * 3 + d) * 9 + kk * 3 + l] = a;
-                                }
-                } else {
-                    tg_generic_tangent(b.material, mp + (int64_t)qq * qs, H, w, ad);
-                }
-            }
-            __syncwarp();
-            ws_mbar_arrive(&bars[team][sg][0]);                             // release: the stage is full
-        }
-        return;
-    }
-
-    // ====================================================================== consumers: phase 2 of elements 2 c, 2 c + 1
-    const int c = role - 1;
-    const int tig_o = gid >> 1, jcol = gid & 1;
-    const int lB = tig < 3 ? tig : 2;
-    const int offA1 = gid * 3 + lB;
-    int cB[5], io27[4];
-#pragma unroll
-    for (int nt = 0; nt < 5; ++nt) {
-        const int dk = 2 * nt + jcol;
-        cB[nt] = (dk < 8 ? dk : 8) * 3 + lB;
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int i = (tig_o - r) & 3;
-        io27[r] = 27 * (i < 3 ? i : 2);
-    }
-    const bool sel0 = (tig == 3), sel1 = (tig == 0 || tig == 3), sel2 = (tig == 2);
-    int offAop[6];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int r0 = sel0 ? 1 : 0, r1 = sel1 ? 2 : 1, r2 = sel2 ? 2 : 3;
-        offAop[3 * h + 0] = (4 * h + r0) * TG_GQ + gid * 3 + ((tig - r0) & 3);
-        offAop[3 * h + 1] = (4 * h + r1) * TG_GQ + gid * 3 + ((tig - r1) & 3);
-        offAop[3 * h + 2] = (4 * h + r2) * TG_GQ + gid * 3 + ((tig - r2) & 3);
-    }
-    for (int64_t k = 0; k < n_mine; ++k) {
-        const int sg = (int)(k & 1);
-        const int64_t grp = first + k * n_teams;
-        const int64_t ev = 4 * grp + 2 * c;
-        while (!ws_mbar_try_wait(&bars[team][sg][0], (uint32_t)((k >> 1) & 1))) {}
-        double* Gw = reinterpret_cast<double*>(tbase + (size_t)sg * WS_STAGE);
-        double* Aw = Gw + 4 * TG_GE;
-        if (ev < b.E) {
-            const double* Ge[2];
-            double* Ae[2];
-            double C[2][9][2];
-#pragma unroll
-            for (int p = 0; p < 2; ++p) {
-                Ge[p] = Gw + (2 * c + p) * TG_GE;
-                Ae[p] = Aw + (2 * c + p) * TG_AE;
-#pragma unroll
-                for (int dk = 0; dk < 9; ++dk) C[p][dk][0] = C[p][dk][1] = 0.0;
-            }
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                double Y[2][4][5][2];
-                auto product1 = [&](int r) {
-                    const int q = 4 * h + r;
-#pragma unroll
-                    for (int p = 0; p < 2; ++p) {
-                        double a1 = Ge[p][q * TG_GQ + offA1];
-                        if (tig == 3) a1 = 0.0;
-                        const double* Aq = Ae[p] + q * TG_AQ + io27[r];
-#pragma unroll
-                        for (int nt = 0; nt < 5; ++nt) {
-                            Y[p][r][nt][0] = Y[p][r][nt][1] = 0.0;
-                            dmma884(Y[p][r][nt][0], Y[p][r][nt][1], a1, Aq[cB[nt]]);
-                        }
-                    }
-                };
-                auto product2 = [&](int st, bool sel, int ra, int rb) {
-#pragma unroll
-                    for (int p = 0; p < 2; ++p) {
-                        const double aop = Ge[p][offAop[3 * h + st]];
-#pragma unroll
-                        for (int dk = 0; dk < 9; ++dk) {
-                            const double y = sel ? Y[p][ra][dk >> 1][dk & 1] : Y[p][rb][dk >> 1][dk & 1];
-                            dmma884(C[p][dk][0], C[p][dk][1], aop, y);
-                        }
-                    }
-                };
-                product1(0);
-                product1(1);
-                product2(0, sel0, 1, 0);
-                product1(2);
-                product2(1, sel1, 2, 1);
-                product1(3);
-                product2(2, sel2, 2, 3);
-            }
-            __syncwarp();
-#pragma unroll
-            for (int p = 0; p < 2; ++p) {
-                double2* st = reinterpret_cast<double2*>(Ae[p] + (gid * 8 + 2 * tig) * 9);
-                st[0] = make_double2(C[p][0][0], C[p][1][0]);
-                st[1] = make_double2(C[p][2][0], C[p][3][0]);
-                st[2] = make_double2(C[p][4][0], C[p][5][0]);
-                st[3] = make_double2(C[p][6][0], C[p][7][0]);
-                st[4] = make_double2(C[p][8][0], C[p][0][1]);
-                st[5] = make_double2(C[p][1][1], C[p][2][1]);
-                st[6] = make_double2(C[p][3][1], C[p][4][1]);
-                st[7] = make_double2(C[p][5][1], C[p][6][1]);
-                st[8] = make_double2(C[p][7][1], C[p][8][1]);
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) {
-#pragma unroll
-                for (int p = 0; p < 2; ++p)
-                    if (ev + p < b.E) {
-                        const unsigned src = (unsigned)__cvta_generic_to_shared(Ae[p]);
-                        double* dst = K_e + (ev + p) * 576;
-                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 4608;" ::"l"(dst), "r"(src) : "memory");
-                    }
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the stage may be refilled after this
-            }
-        }
-        __syncwarp();
-        ws_mbar_arrive(&bars[team][sg][1]);
-    }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    __syncwarp();
-}
-
 // K_e of any constitutive law on hex8 / 8 points through the tensor-core kernel; FEB200_ERR_UNSUPPORTED for anything else
 // (the caller then uses the scalar kernels).
 int tangent_general_mma(cudaStream_t st, const feb200_batch& b, const double* x_vd, const double* u, const double* mask,
                         const double* values, double* K_e) {
     if (!(b.D == 3 && b.N == 8 && b.Q == 8)) return FEB200_ERR_UNSUPPORTED;
     if (((uintptr_t)K_e & 15) != 0) return FEB200_ERR_UNSUPPORTED;          // bulk stores need 16-byte aligned rows
-    static const bool use_ws = getenv("FEB200_TG_WS") != nullptr;           // A/B switch: warp-specialised variant
-    if (use_ws) {
-        static bool ws_attr = false;
-        if (!ws_attr) {
-            FEB_CUDA(cudaFuncSetAttribute(k_tangent_general_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM));
-            ws_attr = true;
-        }
-        const int64_t want_ws = ceil_div(ceil_div(b.E, 4), WS_TEAMS);
-        const int grid_ws = (int)(want_ws < sm_count() ? want_ws : sm_count());
-        k_tangent_general_ws<<<grid_ws, 3 * WS_TEAMS * 32, WS_SMEM, st>>>(b, x_vd, u, mask, values, K_e);
-        return FEB200_OK;
-    }
     static int warps = 0;                                                   // FEB200_TG_WARPS: fewer workers per SM (profile drivers)
     if (warps == 0) {
         const char* env = getenv("FEB200_TG_WARPS");
