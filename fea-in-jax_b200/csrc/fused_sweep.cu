@@ -46,6 +46,9 @@
 // COLS: local node of accumulator column 0..7 (a lane holds columns 2 * tig and 2 * tig + 1 of every column tile);
 // PAD: start of slot s modulo 16 doubles (-1: wherever the previous slot ends) -- both chosen so that the 16 lanes of a half-warp (4 rows x 4 column
 // pairs) spread over the 16 eight-byte banks on structured grids (profiles/r02_panel_layout_search.txt).
+#ifndef FEB_SW_EXCH
+#define FEB_SW_EXCH 1             /* 1 = read-and-clear of a retiring panel entry as one shared-memory exchange */
+#endif
 #ifndef FEB_SW_BS
 #define FEB_SW_BS 9
 #endif
@@ -436,8 +439,13 @@ k_fused_hex8_sweep(feb200_batch b, feb200_sweep_plan plan, SwSmem L, const doubl
                             for (int d = 0; d < 3; ++d)
 #pragma unroll
                                 for (int kk = 0; kk < 3; ++kk) {
+#if FEB_SW_EXCH
+                                    S[d * 3 + kk] = __longlong_as_double((long long)atomicExch(
+                                        reinterpret_cast<unsigned long long*>(src + d * FEB_SW_DS + kk * FEB_SW_KK), 0ull));
+#else
                                     S[d * 3 + kk] = src[d * FEB_SW_DS + kk * FEB_SW_KK];
                                     src[d * FEB_SW_DS + kk * FEB_SW_KK] = 0.0;
+#endif
                                 }
                             const double tr = u_mu * (S[0] + S[4] + S[8]);
 #pragma unroll
