@@ -46,6 +46,9 @@
 // COLS: local node of accumulator column 0..7 (a lane holds columns 2 * tig and 2 * tig + 1 of every column tile);
 // PAD: start of slot s modulo 16 doubles (-1: wherever the previous slot ends) -- both chosen so that the 16 lanes of a half-warp (4 rows x 4 column
 // pairs) spread over the 16 eight-byte banks on structured grids (profiles/r02_panel_layout_search.txt).
+#ifndef FEB_SW_ROT
+#define FEB_SW_ROT 1              /* rotation of the node order per component in the fragment buffer */
+#endif
 #ifndef FEB_SW_EXCH
 #define FEB_SW_EXCH 1             /* 1 = read-and-clear of a retiring panel entry as one shared-memory exchange */
 #endif
@@ -129,10 +132,11 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // Row of (node n, component d) in an element's fragment buffer: component-major, the nodes of a component permuted so
-// that antipodal nodes share a residue mod 4 and the residues rotate by 2 per component: the four rows a half-warp
-// loads at once (four nodes of a face with one component, or two nodes with two components) then fall into distinct
-// 4-double bank groups.
-__device__ __forceinline__ int sw_grow(int n, int d) { return 8 * d + (((n < 4 ? n : 11 - n) + 2 * d) & 7); }
+// that antipodal nodes share a residue mod 4 and the residues rotate by FEB_SW_ROT per component.  With two-node row tiles a
+// half-warp loads the three component rows of ONE node at once: rotation 1 puts them into distinct 4-double bank groups
+// (rotation 2, chosen for the older three-node tiles, made components 0 and 2 collide: 4 instead of 2 wavefronts per A-fragment
+// load, 10.77 -> 10.70 ms at 200^3).  The 8 rows of a component (B fragments) are a permutation of 8 consecutive rows either way.
+__device__ __forceinline__ int sw_grow(int n, int d) { return 8 * d + (((n < 4 ? n : 11 - n) + FEB_SW_ROT * d) & 7); }
 
 // Row tiles 0..NMT-1 of one visit, in three stages so that two independent visits can be interleaved (sweep_pair).
 // Rows: the visit's in-window nodes in ascending local order, two per row tile (rows 0-2 / 4-6 = the three components of a
@@ -367,7 +371,7 @@ k_fused_hex8_sweep(feb200_batch b, feb200_sweep_plan plan, SwSmem L, const doubl
 #pragma unroll
                 for (int n = 0; n < 8; ++n)
 #pragma unroll
-                    for (int d = 0; d < 3; ++d) dst[(8 * d + (((n < 4 ? n : 11 - n) + 2 * d) & 7)) * 4] = gr[n * 3 + d];
+                    for (int d = 0; d < 3; ++d) dst[sw_grow(n, d) * 4] = gr[n * 3 + d];
                 double w = dt * s_w[qq];
                 if (WM == 1) w *= eqbuf[jj * 8] * half_inv;
                 if (WM == 2) w *= eqbuf[jj * 8 + qq] * half_inv;
