@@ -8,11 +8,13 @@
 // (19 008 multiply-adds per element in the factorised form below, plus A_q).  The scalar kernel k_tangent_general_ct ran
 // this at a third of the FP64 peak: one thread per block row, 255 registers, the 81 entries of A_q re-read by every row.
 //
-// Here every warp is an independent worker (no block barrier after start-up) that takes groups of 4 elements:
-//   phase 1  lane = (element, quadrature point): coordinates / solution from the vertex arrays (Dirichlet blend fused),
-//            J, J^-1, the 24 physical gradients, H, then w A_q (closed form for St. Venant-Kirchhoff, forward-mode duals
-//            on the constitutive law otherwise) into shared memory;
-//   phase 2  per element, two chained tensor-core products (mma.sync.m8n8k4.f64), nothing scalar in between:
+// Here every warp is an independent worker (12 per SM, no block barrier after start-up) that takes groups of 4 elements:
+//   phase 1  lane = (element, quadrature point): coordinates / solution from the vertex arrays (Dirichlet blend fused) into
+//            shared memory, J, J^-1, the 24 physical gradients (stored as they are formed), H; then, for two elements at a time,
+//            w A_q (closed form for St. Venant-Kirchhoff, forward-mode duals on the constitutive law otherwise) into shared
+//            memory -- the lanes of the other two elements keep H and w in registers until their turn;
+//   phase 2  per element (two elements run as one instruction stream), two chained tensor-core products
+//            (mma.sync.m8n8k4.f64), nothing scalar in between:
 //              product 1, per point:  Y_q[b][(i,d,k)] = sum_l g_q[b,l] * w A_q[(i,d),(k,l)]          (8 x 27 x 3: 5 DMMAs)
 //              product 2, per (d,k):  K^{dk}[a][b]    = sum_{(q,i)} g_q[a,i] * Y_q[b][(i,d,k)]       (8 x 8 x 24: 6 DMMAs)
 //            The accumulator fragment of product 1 IS the B fragment of product 2: the columns of product 1 are ordered so
@@ -35,9 +37,6 @@
 #endif
 #ifndef FEB_TG_GROUP
 #define FEB_TG_GROUP 4                    /* elements per group (lanes 8 * GROUP .. 31 idle in phase 1 when < 4) */
-#endif
-#ifndef FEB_TG_NOSTORE
-#define FEB_TG_NOSTORE 0                  /* 1 = timing experiment: K_e never leaves the SM */
 #endif
 #ifndef FEB_TG_PAIR
 #define FEB_TG_PAIR 1                     /* 1 = phase 2 runs two elements as one instruction stream */
@@ -328,7 +327,7 @@ k_tangent_general_mma(feb200_batch b, const double* __restrict__ x_vd, const dou
             if (lane == 0) {
 #pragma unroll
                 for (int p = 0; p < TG_NP; ++p)
-                    if (ev + p < b.E && !FEB_TG_NOSTORE) {
+                    if (ev + p < b.E) {
                         const unsigned src = (unsigned)__cvta_generic_to_shared(Ae[p]);
                         double* dst = K_e + (ev + p) * 576;
                         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 4608;" ::"l"(dst), "r"(src) : "memory");
