@@ -237,13 +237,28 @@ FEB_HD void stress_from_C(const double (&C)[VoigtSize<D>::value][VoigtSize<D>::v
         for (int j = 0; j < D; ++j) sig[i][j] = sv[voigt<D>(i, j)];
 }
 
+// isotropic C applied in closed form: S = lam tr(e) I + 2 mu e  (the same numbers as isotropic_C + stress_from_C: C[i][i] =
+// lam + 2 mu, C[i][j] = lam, shear mu on the doubled shear strains; plane stress in 2-D through isotropic_lame<2>)
+template <int D, typename T>
+FEB_HD void isotropic_stress(const double* mp, const T (&e)[D][D], T (&S)[D][D]) {
+    double lam, mu;
+    isotropic_lame<D>(mp, lam, mu);
+    T tr = e[0][0];
+    for (int i = 1; i < D; ++i) tr = tr + e[i][i];
+    const T ltr = tr * lam;
+    const double mu2 = 2.0 * mu;
+    for (int i = 0; i < D; ++i)
+        for (int j = 0; j < D; ++j) {
+            S[i][j] = e[i][j] * mu2;
+            if (i == j) S[i][j] = S[i][j] + ltr;
+        }
+}
+
 // ---------------------------------------------------------------------------------------------
 // hyperelastic "stress" S(F) exactly as the reference returns it (used as is in the residual)
 // ---------------------------------------------------------------------------------------------
 template <int D, typename T>
 FEB_HD void svk_stress(const double* mp, const T (&F)[D][D], T (&S)[D][D]) {
-    double C[VoigtSize<D>::value][VoigtSize<D>::value];
-    isotropic_C<D>(mp, C);
     T egl[D][D];
     for (int i = 0; i < D; ++i)
         for (int j = 0; j < D; ++j) {
@@ -251,7 +266,7 @@ FEB_HD void svk_stress(const double* mp, const T (&F)[D][D], T (&S)[D][D]) {
             for (int d = 1; d < D; ++d) acc = acc + F[d][i] * F[d][j];
             egl[i][j] = (acc - (i == j ? 1.0 : 0.0)) * 0.5;
         }
-    stress_from_C<D, T>(C, egl, S);
+    isotropic_stress<D, T>(mp, egl, S);
 }
 
 template <int D, typename T>
@@ -295,6 +310,13 @@ FEB_HD void mooney_rivlin_stress(const double* mp, const T (&F)[D][D], T (&S)[D]
 // ---------------------------------------------------------------------------------------------
 template <int D, typename T>
 FEB_HD void point_stress(int material, const double* mp, const T (&H)[D][D], T (&S)[D][D]) {
+    if (material == MAT_ISOTROPIC) {
+        T eps[D][D];
+        for (int i = 0; i < D; ++i)
+            for (int j = 0; j < D; ++j) eps[i][j] = (H[i][j] + H[j][i]) * 0.5;
+        isotropic_stress<D, T>(mp, eps, S);
+        return;
+    }
     if (material == MAT_ISOTROPIC || material == MAT_ORTHOTROPIC) {
         double C[VoigtSize<D>::value][VoigtSize<D>::value];
         if (material == MAT_ISOTROPIC) isotropic_C<D>(mp, C);
